@@ -1,0 +1,134 @@
+/* covomix_b200.h -- C ABI of libcovomix_b200.so (CUDA, sm_100a only).
+ *
+ * The reference (vivian556123/NeurIPS2024-CoVoMix) is pure Python on this path and has no FFI layer;
+ * the drop-in boundary is two Python call sites.  Each entry point below cites the reference
+ * interface it replaces (paths relative to the reference root).  The Python binding a maintainer
+ * would add is in INTEGRATION.md; the binding shipped here is neurips2024-covomix_b200/_native.py.
+ *
+ * Conventions: every function returns 0 on success and a negative covo_status on failure; the
+ * message is available from covo_last_error() (thread-local).  Nothing throws across the ABI.
+ * Pointers are DEVICE pointers unless marked host.  Calls only enqueue work on `stream`
+ * (a cudaStream_t passed as void*); they never synchronise the device (the one-time build of a plan
+ * for a new (B, N, solver) shape does host work and a stream capture).  A handle is bound to one
+ * device and is not re-entrant; use one handle per rank.  The caller owns inputs, outputs and the
+ * workspace; the library owns only its copy of the packed weights.
+ */
+#ifndef COVOMIX_B200_H
+#define COVOMIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COVO_ABI_VERSION 1
+
+typedef enum covo_status {
+    COVO_OK = 0,
+    COVO_ERR_INVALID = -1,   /* bad argument / shape / config */
+    COVO_ERR_CUDA = -2,      /* a CUDA runtime or driver call failed */
+    COVO_ERR_WEIGHTS = -3,   /* packed weight blob malformed or a tensor is missing */
+    COVO_ERR_ARCH = -4       /* device is not sm_100 (no fallback path exists) */
+} covo_status;
+
+enum { COVO_ODE_EULER = 0, COVO_ODE_MIDPOINT = 1 };            /* torchdiffeq method= (acoustic.py:572,589) */
+enum { COVO_WAV_F32 = 0, COVO_WAV_F16 = 1, COVO_WAV_I16 = 2 }; /* waveform output dtype */
+enum { COVO_H_BF16 = 0, COVO_H_FP16 = 1 };                     /* 16-bit operand format of the vocoder convs */
+
+/* ---- flow-matching acoustic decoder -------------------------------------------------------------
+ * Mirrors the constructor arguments of CoVoMix (covomix/covomix_model/acoustic.py:326-348) as set by
+ * CoVoMixModel.__init__ (covomix/conditional_model.py:99-115). */
+typedef struct covo_flow_cfg {
+    int32_t dim;                 /* 1024 */
+    int32_t depth;               /* 8 (even) */
+    int32_t heads;               /* 16 */
+    int32_t dim_head;            /* 64 (only value supported) */
+    int32_t dim_in;              /* 80 VoSingle, 160 VoMix: width of `cond` */
+    int32_t dim_x;               /* 80: width of the ODE state / to_pred output */
+    int32_t n_streams;           /* 1: ids [B,N]; 2: ids [B,N,2] (twocondition_oneoutput) */
+    int32_t num_phoneme_tokens;  /* 502; id 502 is the CFG null token (acoustic.py:367) */
+    int32_t dim_phoneme_emb;     /* 1024 */
+    int32_t ff_mult;             /* 4 */
+    int32_t conv_pos_kernel;     /* 31 */
+} covo_flow_cfg;
+
+typedef struct covo_flow covo_flow;
+
+/* packed_weights: HOST pointer to a blob produced by covomix_b200.packing.pack_flow_weights. */
+int covo_flow_create(const covo_flow_cfg* cfg, const void* packed_weights, size_t bytes, int device, covo_flow** out);
+int covo_flow_destroy(covo_flow* h);
+
+/* Bytes of caller-owned scratch needed by covo_flow_sample / covo_flow_velocity for batch B, length N. */
+size_t covo_flow_workspace_bytes(const covo_flow* h, int B, int N, int n_eval_times);
+
+/* Replaces ConditionalFlowMatcherWrapper.sample (acoustic.py:597-688) == CoVoMixModel.synthesis_sample
+ * (conditional_model.py:295-302) with torchdiffeq.odeint's fixed-grid solver inlined:
+ *   ids   int64 [B,N] or [B,N,2]        cond f32 [B,N,dim_in]
+ *   y0    f32 [B,N,dim_x]  (the caller draws it with torch.randn_like, acoustic.py:647-650)
+ *   out   f32 [B,N,dim_x]  x(t=1), prompt rows included (the caller slices with its mask)
+ *   method/n_steps: COVO_ODE_MIDPOINT,16 is the reference default (step_size 0.0625, acoustic.py:568)
+ *   cond_scale: classifier-free guidance scale (acoustic.py:421-428); 1.0 skips the null branch. */
+int covo_flow_sample(covo_flow* h, const int64_t* ids, const float* cond, const float* y0, float* out, int B, int N,
+                     int method, int n_steps, float cond_scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One velocity evaluation  v = CoVoMix.forward_with_cond_scale(x, times=t, ...) (acoustic.py:414-428):
+ * x, v f32 [B,N,dim_x].  Used by parity tests and for the "ODE-step ms" metric. */
+int covo_flow_velocity(covo_flow* h, const int64_t* ids, const float* cond, const float* x, float t, float* v, int B,
+                       int N, float cond_scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels one covo_flow_sample call launches for this configuration (bench.py's gpu_launches). */
+int covo_flow_launches_per_sample(const covo_flow* h, int method, int n_steps, float cond_scale);
+
+/* ---- HiFi-GAN generator ---------------------------------------------------------------------------
+ * Mirrors the fields Generator.__init__ reads from the JSON config (hifi-gan/models.py:76-98,
+ * hifi-gan/config_covomix.json). */
+typedef struct covo_hifigan_cfg {
+    int32_t num_mels;             /* 80 */
+    int32_t upsample_initial_channel;
+    int32_t num_upsamples;        /* <= 8 */
+    int32_t upsample_rates[8];
+    int32_t upsample_kernel_sizes[8];
+    int32_t num_kernels;          /* resblocks per stage, <= 4 */
+    int32_t resblock_kernel_sizes[4];
+    int32_t num_dilations;        /* convs per resblock, <= 4 */
+    int32_t resblock_dilations[4][4];
+    int32_t resblock_type;        /* 1 = ResBlock1 (models.py:11-48), 2 = ResBlock2 (models.py:51-72) */
+    int32_t h_format;             /* COVO_H_BF16 | COVO_H_FP16 */
+} covo_hifigan_cfg;
+
+typedef struct covo_hifigan covo_hifigan;
+
+/* packed_weights: HOST pointer to a blob produced by covomix_b200.packing.pack_hifigan_weights
+ * (weight norm already folded: Generator.remove_weight_norm, models.py:118-125). */
+int covo_hifigan_create(const covo_hifigan_cfg* cfg, const void* packed_weights, size_t bytes, int device,
+                        covo_hifigan** out);
+int covo_hifigan_destroy(covo_hifigan* h);
+size_t covo_hifigan_workspace_bytes(const covo_hifigan* h, int B, int T);
+/* Output samples per item for T mel frames (160*T + 32 for config_covomix.json). */
+int64_t covo_hifigan_out_len(const covo_hifigan* h, int T);
+
+/* Replaces Generator.forward (hifi-gan/models.py:100-116 == covomix/vocoder/models.py):
+ *   mel f32 [B, num_mels, T]  ->  wav [B, out_len(T)] in out_dtype (COVO_WAV_*);
+ *   COVO_WAV_I16 additionally applies mel_decode_to_wav's x32768 + int16 cast
+ *   (monologue_generation.py:52-59). */
+int covo_hifigan_forward(covo_hifigan* h, const float* mel, void* wav, int B, int T, int out_dtype, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int covo_hifigan_launches_per_forward(const covo_hifigan* h);
+
+/* ---- misc ------------------------------------------------------------------------------------------ */
+const char* covo_last_error(void);
+int covo_version(void);
+
+/* ---- kernel-level test hooks (used only by tests/ to check single kernels against torch) -------------
+ * D[M,N] = A[M,K] * W[N,K]^T (+bias) (+residual), bf16 operands, fp32 accumulate, via the tcgen05 kernel. */
+int covo_dbg_gemm(const void* A_bf16, const void* W_bf16, const float* bias, const float* residual, float* out_f32,
+                  void* out_bf16, int M, int N, int K, int act_h, int force_bn, void* stream);
+/* qkv bf16 [Bt, N, 3*heads*64] -> out bf16 [Bt, N, heads*64]; impl 0 = tcgen05 kernel, 1 = naive CUDA-core kernel. */
+int covo_dbg_attention(const void* qkv_bf16, void* out_bf16, int Bt, int N, int heads, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVOMIX_B200_H */

@@ -1,0 +1,283 @@
+// Host-side plumbing shared by the flow sampler and the vocoder: error reporting, packed-weight blob,
+// TMA tensor-map encoding, GEMM op construction/launch.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/covomix_b200.h"
+#include "attention_sm100.cuh"
+#include "gemm_sm100.cuh"
+#include "kernels.cuh"
+
+namespace covo {
+
+// ------------------------------------------------------------------------------------------------ errors
+inline std::string& err_slot() {
+    static thread_local std::string s;
+    return s;
+}
+inline int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err_slot() = buf;
+    return code;
+}
+#define COVO_CK(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return ::covo::fail(COVO_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define COVO_TRY(expr)              \
+    do {                            \
+        int rc_ = (expr);           \
+        if (rc_ != COVO_OK) return rc_; \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// ------------------------------------------------------------------------------------------------ weights blob
+// Layout (little endian), written by covomix_b200.packing:
+//   header : char magic[8] = "COVOWTS1"; u32 n_entries; u32 reserved
+//   entries: n x { char name[48]; u32 dtype; u32 ndim; u64 shape[4]; u64 offset; u64 nbytes }
+//   data   : tensors at `offset` bytes from the blob start (256-byte aligned)
+enum : uint32_t { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2, DT_I64 = 3 };
+struct BlobEntry {
+    char name[48];
+    uint32_t dtype, ndim;
+    uint64_t shape[4];
+    uint64_t offset, nbytes;
+};
+struct Tensor {
+    void* ptr = nullptr;
+    uint32_t dtype = 0, ndim = 0;
+    uint64_t shape[4] = {0, 0, 0, 0};
+    template <class T>
+    T* as() const { return static_cast<T*>(ptr); }
+};
+struct Weights {
+    void* dev = nullptr;
+    size_t bytes = 0;
+    std::map<std::string, Tensor> t;
+
+    int load(const void* host_blob, size_t nbytes) {
+        if (nbytes < 16 || memcmp(host_blob, "COVOWTS1", 8) != 0) return fail(COVO_ERR_WEIGHTS, "bad weight blob magic");
+        const uint8_t* p = static_cast<const uint8_t*>(host_blob);
+        uint32_t n;
+        memcpy(&n, p + 8, 4);
+        if (16 + static_cast<size_t>(n) * sizeof(BlobEntry) > nbytes) return fail(COVO_ERR_WEIGHTS, "weight blob truncated");
+        COVO_CK(cudaMalloc(&dev, nbytes));
+        COVO_CK(cudaMemcpy(dev, host_blob, nbytes, cudaMemcpyHostToDevice));
+        bytes = nbytes;
+        for (uint32_t i = 0; i < n; ++i) {
+            BlobEntry e;
+            memcpy(&e, p + 16 + static_cast<size_t>(i) * sizeof(BlobEntry), sizeof(BlobEntry));
+            if (e.offset + e.nbytes > nbytes || (e.offset & 255)) return fail(COVO_ERR_WEIGHTS, "entry %u out of range", i);
+            Tensor tt;
+            tt.ptr = static_cast<uint8_t*>(dev) + e.offset;
+            tt.dtype = e.dtype;
+            tt.ndim = e.ndim;
+            memcpy(tt.shape, e.shape, sizeof(tt.shape));
+            e.name[47] = 0;
+            t[e.name] = tt;
+        }
+        return COVO_OK;
+    }
+    int get(const std::string& name, uint32_t dtype, Tensor* out) const {
+        auto it = t.find(name);
+        if (it == t.end()) return fail(COVO_ERR_WEIGHTS, "packed weights: tensor '%s' missing", name.c_str());
+        if (it->second.dtype != dtype)
+            return fail(COVO_ERR_WEIGHTS, "packed weights: tensor '%s' has dtype %u, expected %u", name.c_str(),
+                        it->second.dtype, dtype);
+        *out = it->second;
+        return COVO_OK;
+    }
+    void release() {
+        if (dev) cudaFree(dev);
+        dev = nullptr;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// 16-bit tensor, innermost dim contiguous; strides (bytes) for dims 1..rank-1; 128B swizzle.
+inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int is_fp16) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(COVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) {
+            gstr[i - 1] = strides_bytes[i - 1];
+            if (gstr[i - 1] % 16) return fail(COVO_ERR_INVALID, "TMA stride %llu not 16-byte aligned", (unsigned long long)gstr[i - 1]);
+        }
+    }
+    if (reinterpret_cast<uintptr_t>(base) % 16) return fail(COVO_ERR_INVALID, "TMA base not 16-byte aligned");
+    CUresult r = fn(tm, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(COVO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return COVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM ops
+struct DeviceInfo {
+    int device = 0;
+    int num_sms = 148;
+};
+
+struct ASource {             // 16-bit activations [Z][rows][K], K contiguous
+    const void* ptr;
+    int K;                   // multiple of 64 (padded columns are zero)
+    int rows;
+    int Z;
+    long long row_stride;    // elements
+    long long z_stride;      // elements
+};
+
+struct GemmOp {
+    GemmArgs args;
+    int bn = 256;
+    int fmt = 1;             // 0 fp16, 1 bf16
+    int grid = 1;
+};
+
+template <int BN, int FMT>
+inline int set_gemm_attr() {
+    static bool done = false;
+    if (!done) {
+        COVO_CK(cudaFuncSetAttribute(gemm_tc_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmCfg<BN>::SMEM_BYTES));
+        done = true;
+    }
+    return COVO_OK;
+}
+
+inline int pick_bn(int n_pad, long long m_tiles, int num_sms, int force_bn) {
+    if (force_bn) return force_bn;
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        if (n_pad % bn) continue;
+        if (m_tiles * (n_pad / bn) >= num_sms) return bn;
+    }
+    for (int i = 2; i >= 0; --i)
+        if (n_pad % cands[i] == 0) return cands[i];
+    return 0;
+}
+
+// Fills tensor maps, tile counts and grid.  Epilogue/output-mapping fields of op.args must be set by the caller
+// (before or after; this function touches only tmA/tmB/rows/Z/n_tiles/taps/kc_per_tap and bn/grid/fmt).
+inline int build_gemm(GemmOp& op, const DeviceInfo& di, const ASource& a, int q_rows, int q_Z, const void* w, int n_pad,
+                      int taps, int is_fp16, int force_bn = 0) {
+    if (a.K % GEMM_BK) return fail(COVO_ERR_INVALID, "GEMM K=%d not a multiple of %d", a.K, GEMM_BK);
+    if (taps < 1 || taps > GEMM_MAX_TAPS) return fail(COVO_ERR_INVALID, "GEMM taps=%d out of range", taps);
+    const long long m_tiles = static_cast<long long>(q_Z) * ceil_div(q_rows, GEMM_BM);
+    op.bn = pick_bn(n_pad, m_tiles, di.num_sms, force_bn);
+    if (op.bn == 0 || n_pad % op.bn) return fail(COVO_ERR_INVALID, "GEMM N_pad=%d not tileable", n_pad);
+    op.fmt = is_fp16 ? 0 : 1;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.rows), static_cast<uint64_t>(a.Z)};
+        uint64_t str[2] = {static_cast<uint64_t>(a.row_stride) * 2, static_cast<uint64_t>(a.z_stride) * 2};
+        if (a.Z == 1) str[1] = static_cast<uint64_t>(a.row_stride) * 2 * static_cast<uint64_t>(a.rows > 0 ? a.rows : 1);
+        uint32_t box[3] = {GEMM_BK, GEMM_BM, 1};
+        COVO_TRY(make_tmap(&op.args.tmA, a.ptr, 3, dims, str, box, is_fp16));
+    }
+    {
+        const int ktot = taps * a.K;
+        uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(n_pad)};
+        uint64_t str[1] = {static_cast<uint64_t>(ktot) * 2};
+        uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(op.bn)};
+        COVO_TRY(make_tmap(&op.args.tmB, w, 2, dims, str, box, is_fp16));
+    }
+    op.args.rows = q_rows;
+    op.args.Z = q_Z;
+    op.args.n_tiles = n_pad / op.bn;
+    op.args.taps = taps;
+    op.args.kc_per_tap = a.K / GEMM_BK;
+    const long long tiles = m_tiles * op.args.n_tiles;
+    op.grid = static_cast<int>(tiles < di.num_sms ? tiles : di.num_sms);
+    if (op.grid < 1) op.grid = 1;
+    return COVO_OK;
+}
+
+inline void gemm_defaults(GemmArgs& g) {
+    memset(&g, 0, sizeof(g));
+    g.up_s = 1;
+    g.up_p = 0;
+    g.phase_w = 1 << 30;
+    g.slope = 0.1f;
+}
+
+inline int launch_gemm(const GemmOp& op, cudaStream_t st) {
+#define COVO_LAUNCH(BN_, F_)                                                                              \
+    do {                                                                                                  \
+        COVO_TRY((set_gemm_attr<BN_, F_>()));                                                             \
+        gemm_tc_kernel<BN_, F_><<<op.grid, GEMM_THREADS, GemmCfg<BN_>::SMEM_BYTES, st>>>(op.args);        \
+    } while (0)
+    if (op.fmt == 1) {
+        if (op.bn == 256) COVO_LAUNCH(256, 1);
+        else if (op.bn == 128) COVO_LAUNCH(128, 1);
+        else COVO_LAUNCH(64, 1);
+    } else {
+        if (op.bn == 256) COVO_LAUNCH(256, 0);
+        else if (op.bn == 128) COVO_LAUNCH(128, 0);
+        else COVO_LAUNCH(64, 0);
+    }
+#undef COVO_LAUNCH
+    COVO_CK(cudaGetLastError());
+    return COVO_OK;
+}
+
+// bump allocator over the caller's workspace
+struct Arena {
+    uint8_t* base;
+    size_t cap, off = 0;
+    Arena(void* p, size_t c) : base(static_cast<uint8_t*>(p)), cap(c) {}
+    template <class T>
+    T* take(size_t n) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base ? base + off : nullptr);
+        off += n * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+inline int check_device(int device, DeviceInfo* di) {
+    cudaDeviceProp p;
+    COVO_CK(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return fail(COVO_ERR_ARCH, "device %d is sm_%d%d; this library is sm_100a only", device, p.major, p.minor);
+    di->device = device;
+    di->num_sms = p.multiProcessorCount;
+    return COVO_OK;
+}
+
+}  // namespace covo

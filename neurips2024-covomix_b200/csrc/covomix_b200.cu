@@ -1,0 +1,270 @@
+// libcovomix_b200.so -- C ABI (include/covomix_b200.h) over the sm_100a kernels.
+#include "flow.cuh"
+#include "hifigan.cuh"
+
+using namespace covo;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int init_kernel_attrs() {
+    COVO_TRY((set_gemm_attr<256, 1>()));
+    COVO_TRY((set_gemm_attr<128, 1>()));
+    COVO_TRY((set_gemm_attr<64, 1>()));
+    COVO_TRY((set_gemm_attr<256, 0>()));
+    COVO_TRY((set_gemm_attr<128, 0>()));
+    COVO_TRY((set_gemm_attr<64, 0>()));
+    COVO_CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    return COVO_OK;
+}
+
+bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* covo_last_error(void) { return err_slot().c_str(); }
+int covo_version(void) { return COVO_ABI_VERSION; }
+
+// ====================================================================================== flow
+int covo_flow_create(const covo_flow_cfg* cfg, const void* packed_weights, size_t bytes, int device, covo_flow** out) {
+    if (!cfg || !packed_weights || !out) return fail(COVO_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->dim_head != 64) return fail(COVO_ERR_INVALID, "dim_head=%d unsupported (64 only)", cfg->dim_head);
+    if (cfg->depth < 2 || cfg->depth % 2) return fail(COVO_ERR_INVALID, "depth=%d must be even", cfg->depth);
+    if (cfg->dim % 128 || cfg->dim > 1024) return fail(COVO_ERR_INVALID, "dim=%d unsupported (128..1024, multiple of 128)", cfg->dim);
+    if (cfg->n_streams != 1 && cfg->n_streams != 2) return fail(COVO_ERR_INVALID, "n_streams=%d", cfg->n_streams);
+    if (cfg->conv_pos_kernel != 31) return fail(COVO_ERR_INVALID, "conv_pos_kernel=%d unsupported (31 only)", cfg->conv_pos_kernel);
+    if (cfg->dim_x % 2) return fail(COVO_ERR_INVALID, "dim_x=%d must be even", cfg->dim_x);
+    DeviceGuard g(device);
+    covo_flow* h = new covo_flow();
+    h->cfg = *cfg;
+    int rc = check_device(device, &h->di);
+    if (rc == COVO_OK) rc = init_kernel_attrs();
+    if (rc == COVO_OK) rc = h->w.load(packed_weights, bytes);
+    if (rc == COVO_OK) rc = flow_bind_weights(h);
+    if (rc == COVO_OK && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess)
+        rc = fail(COVO_ERR_CUDA, "cudaStreamCreate failed");
+    if (rc != COVO_OK) {
+        h->w.release();
+        delete h;
+        return rc;
+    }
+    h->use_graph = !env_flag("COVO_NO_GRAPH");
+    h->naive_attn = env_flag("COVO_DEBUG_NAIVE_ATTN");
+    *out = h;
+    return COVO_OK;
+}
+
+int covo_flow_destroy(covo_flow* h) {
+    if (!h) return COVO_OK;
+    DeviceGuard g(h->di.device);
+    cudaDeviceSynchronize();
+    for (FlowPlan* p : h->plans) flow_free_plan(p);
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+    h->w.release();
+    delete h;
+    return COVO_OK;
+}
+
+size_t covo_flow_workspace_bytes(const covo_flow* h, int B, int N, int n_eval_times) {
+    if (!h || B < 1 || N < 1) return 0;
+    FlowPlan p;
+    p.B = B;
+    p.N = N;
+    p.BN = B * N;
+    p.M = 2 * p.BN;
+    p.n_t = n_eval_times < 1 ? 1 : (n_eval_times > FLOW_MAX_TIMES ? FLOW_MAX_TIMES : n_eval_times);
+    p.ws = nullptr;
+    return flow_layout(h, p);
+}
+
+int covo_flow_launches_per_sample(const covo_flow* h, int method, int n_steps, float cond_scale) {
+    if (!h) return 0;
+    (void)cond_scale;
+    const int half = h->cfg.depth / 2;
+    const int per_net = 2 + 7 * h->cfg.depth + half + 2;
+    const int nfe = flow_num_times(method, n_steps);
+    return 7 + 1 + nfe * (per_net + 1);
+}
+
+int covo_flow_sample(covo_flow* h, const int64_t* ids, const float* cond, const float* y0, float* out, int B, int N,
+                     int method, int n_steps, float cond_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !ids || !cond || !y0 || !out) return fail(COVO_ERR_INVALID, "null argument");
+    DeviceGuard g(h->di.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FlowPlan* p = nullptr;
+    COVO_TRY(flow_get_plan(h, B, N, method, n_steps, cond_scale, 0, workspace, workspace_bytes, &p));
+    const covo_flow_cfg& c = h->cfg;
+    const size_t bn = static_cast<size_t>(B) * N;
+    COVO_CK(cudaMemcpyAsync(p->ids, ids, bn * c.n_streams * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    COVO_CK(cudaMemcpyAsync(p->cond, cond, bn * c.dim_in * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    COVO_CK(cudaMemcpyAsync(p->x_state, y0, bn * c.dim_x * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (p->exec) {
+        COVO_CK(cudaGraphLaunch(p->exec, st));
+    } else {
+        int launches = 0;
+        COVO_TRY(flow_enqueue_sample(h, *p, st, &launches));
+        p->launches = launches;
+    }
+    COVO_CK(cudaMemcpyAsync(out, p->x_state, bn * c.dim_x * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return COVO_OK;
+}
+
+int covo_flow_velocity(covo_flow* h, const int64_t* ids, const float* cond, const float* x, float t, float* v, int B,
+                       int N, float cond_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !ids || !cond || !x || !v) return fail(COVO_ERR_INVALID, "null argument");
+    DeviceGuard g(h->di.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FlowPlan* p = nullptr;
+    COVO_TRY(flow_get_plan(h, B, N, COVO_ODE_EULER, 1, cond_scale, 1, workspace, workspace_bytes, &p));
+    const covo_flow_cfg& c = h->cfg;
+    const size_t bn = static_cast<size_t>(B) * N;
+    p->times[0] = t;
+    COVO_CK(cudaMemcpyAsync(p->ids, ids, bn * c.n_streams * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    COVO_CK(cudaMemcpyAsync(p->cond, cond, bn * c.dim_in * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    COVO_CK(cudaMemcpyAsync(p->x_in, x, bn * c.dim_x * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    int launches = 0;
+    COVO_TRY(flow_enqueue_velocity(h, *p, st, &launches));
+    COVO_CK(cudaMemcpyAsync(v, p->v_out, bn * c.dim_x * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return COVO_OK;
+}
+
+// ====================================================================================== hifigan
+int covo_hifigan_create(const covo_hifigan_cfg* cfg, const void* packed_weights, size_t bytes, int device,
+                        covo_hifigan** out) {
+    if (!cfg || !packed_weights || !out) return fail(COVO_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->num_upsamples < 1 || cfg->num_upsamples > 8) return fail(COVO_ERR_INVALID, "num_upsamples=%d", cfg->num_upsamples);
+    if (cfg->num_kernels < 1 || cfg->num_kernels > 3) return fail(COVO_ERR_INVALID, "num_kernels=%d (1..3 supported)", cfg->num_kernels);
+    if (cfg->num_dilations < 1 || cfg->num_dilations > 4) return fail(COVO_ERR_INVALID, "num_dilations=%d", cfg->num_dilations);
+    if (cfg->resblock_type != 1 && cfg->resblock_type != 2) return fail(COVO_ERR_INVALID, "resblock_type=%d", cfg->resblock_type);
+    for (int i = 0; i < cfg->num_upsamples; ++i) {
+        const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+        if (u < 1 || k < u || (k + u - 1) / u > GEMM_MAX_TAPS) return fail(COVO_ERR_INVALID, "upsample %d: rate %d kernel %d unsupported", i, u, k);
+    }
+    for (int j = 0; j < cfg->num_kernels; ++j)
+        if (cfg->resblock_kernel_sizes[j] > GEMM_MAX_TAPS || cfg->resblock_kernel_sizes[j] % 2 == 0)
+            return fail(COVO_ERR_INVALID, "resblock kernel size %d unsupported (odd, <= %d)", cfg->resblock_kernel_sizes[j], GEMM_MAX_TAPS);
+    DeviceGuard g(device);
+    covo_hifigan* h = new covo_hifigan();
+    h->cfg = *cfg;
+    h->is_fp16 = cfg->h_format == COVO_H_FP16;
+    h->mel_pad = pad64(cfg->num_mels);
+    int rc = check_device(device, &h->di);
+    if (rc == COVO_OK) rc = init_kernel_attrs();
+    if (rc == COVO_OK) rc = h->w.load(packed_weights, bytes);
+    if (rc != COVO_OK) {
+        h->w.release();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return COVO_OK;
+}
+
+int covo_hifigan_destroy(covo_hifigan* h) {
+    if (!h) return COVO_OK;
+    DeviceGuard g(h->di.device);
+    cudaDeviceSynchronize();
+    for (HifiPlan* p : h->plans) delete p;
+    h->w.release();
+    delete h;
+    return COVO_OK;
+}
+
+size_t covo_hifigan_workspace_bytes(const covo_hifigan* h, int B, int T) {
+    if (!h || B < 1 || T < 1) return 0;
+    HifiPlan p;
+    p.B = B;
+    p.T = T;
+    p.ws = nullptr;
+    return hifi_layout(h, p);
+}
+
+int64_t covo_hifigan_out_len(const covo_hifigan* h, int T) { return h ? hifi_out_len(h->cfg, T) : 0; }
+
+int covo_hifigan_launches_per_forward(const covo_hifigan* h) {
+    if (!h) return 0;
+    const covo_hifigan_cfg& c = h->cfg;
+    const int per_rb = c.num_dilations * (c.resblock_type == 1 ? 2 : 1);
+    return 2 + c.num_upsamples * (1 + c.num_kernels * per_rb + 1) + 1;
+}
+
+int covo_hifigan_forward(covo_hifigan* h, const float* mel, void* wav, int B, int T, int out_dtype, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (!h || !mel || !wav) return fail(COVO_ERR_INVALID, "null argument");
+    if (out_dtype < COVO_WAV_F32 || out_dtype > COVO_WAV_I16) return fail(COVO_ERR_INVALID, "out_dtype=%d", out_dtype);
+    DeviceGuard g(h->di.device);
+    HifiPlan* p = nullptr;
+    COVO_TRY(hifi_get_plan(h, B, T, workspace, workspace_bytes, &p));
+    return hifi_enqueue(h, *p, mel, wav, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+// ====================================================================================== test hooks
+int covo_dbg_gemm(const void* A_bf16, const void* W_bf16, const float* bias, const float* residual, float* out_f32,
+                  void* out_bf16, int M, int N, int K, int act_h, int force_bn, void* stream) {
+    int dev = 0;
+    COVO_CK(cudaGetDevice(&dev));
+    DeviceInfo di;
+    COVO_TRY(check_device(dev, &di));
+    COVO_TRY(init_kernel_attrs());
+    if (N % 64 || K % 64) return fail(COVO_ERR_INVALID, "dbg_gemm needs N, K multiples of 64");
+    GemmOp op;
+    gemm_defaults(op.args);
+    COVO_TRY(build_gemm(op, di, a2d(A_bf16, K, M), M, 1, W_bf16, N, 1, 0, force_bn));
+    plain_out(op.args, M, N, N);
+    op.args.bias = bias;
+    op.args.residual = residual;
+    op.args.out_f32 = out_f32;
+    op.args.out_h = out_bf16;
+    op.args.act_h = act_h;
+    return launch_gemm(op, static_cast<cudaStream_t>(stream));
+}
+
+int covo_dbg_attention(const void* qkv_bf16, void* out_bf16, int Bt, int N, int heads, int impl, void* stream) {
+    int dev = 0;
+    COVO_CK(cudaGetDevice(&dev));
+    DeviceInfo di;
+    COVO_TRY(check_device(dev, &di));
+    COVO_TRY(init_kernel_attrs());
+    const int inner = heads * 64;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (impl == 1) {
+        dim3 grid(ceil_div(N, 8), heads, Bt);
+        naive_attention_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
+                                                     static_cast<__nv_bfloat16*>(out_bf16), N, heads, inner, 0.125f);
+    } else {
+        AttnArgs a;
+        uint64_t dims[3] = {static_cast<uint64_t>(3 * inner), static_cast<uint64_t>(N), static_cast<uint64_t>(Bt)};
+        uint64_t str[2] = {static_cast<uint64_t>(3 * inner) * 2, static_cast<uint64_t>(3 * inner) * 2 * N};
+        uint32_t box[3] = {64, 128, 1};
+        COVO_TRY(make_tmap(&a.tmQKV, qkv_bf16, 3, dims, str, box, 0));
+        a.out = static_cast<__nv_bfloat16*>(out_bf16);
+        a.N = N;
+        a.heads = heads;
+        a.inner = inner;
+        a.scale_log2e = 1.4426950408889634f * 0.125f;
+        dim3 grid(ceil_div(N, ATT_BM), heads, Bt);
+        attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+    }
+    COVO_CK(cudaGetLastError());
+    return COVO_OK;
+}
+
+}  // extern "C"

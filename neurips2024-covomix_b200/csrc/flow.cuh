@@ -1,0 +1,504 @@
+// Flow-matching acoustic decoder: host-side plan (buffers, GEMM ops, CUDA graph) for
+// ConditionalFlowMatcherWrapper.sample / CoVoMix.forward_with_cond_scale (covomix/covomix_model/acoustic.py).
+#pragma once
+#include "common.cuh"
+
+namespace covo {
+
+constexpr int FLOW_MAX_TIMES = 128;
+struct TimesArg {
+    float t[FLOW_MAX_TIMES];
+};
+__global__ void set_times_kernel(float* out, TimesArg ta, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ta.t[i];
+}
+
+struct FlowLayerW {
+    Tensor skip_w, skip_b;          // layers >= depth/2
+    Tensor qkv_w, out_w, ff1_w, ff1_b, ff2_w, ff2_b;
+};
+
+struct FlowPlan {
+    // key
+    int B = 0, N = 0, method = 0, n_steps = 0, single_eval = 0;
+    float cond_scale = 0.f;
+    void* ws = nullptr;
+    // derived
+    int two_branch = 1, M = 0, BN = 0, n_t = 0;
+    float times[FLOW_MAX_TIMES];
+    float dts[FLOW_MAX_TIMES];
+    // workspace buffers
+    long long* ids = nullptr;
+    float *cond = nullptr, *x_state = nullptr, *x_in = nullptr, *v_out = nullptr;
+    float *d_times = nullptr, *tfeat = nullptr, *temb = nullptr, *gb = nullptr;
+    float2* rope = nullptr;
+    __nv_bfloat16 *a_pc = nullptr, *xin = nullptr, *slots = nullptr, *a_norm = nullptr, *qkv = nullptr, *attn_o = nullptr,
+                  *ffh = nullptr;
+    float *e_const = nullptr, *h0 = nullptr, *x = nullptr, *vpred = nullptr;
+    // ops
+    GemmOp op_const, op_embed, op_pred;
+    std::vector<GemmOp> op_skip, op_qkv, op_out, op_ff1, op_ff2;
+    AttnArgs attn;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+};
+
+}  // namespace covo
+
+struct covo_flow {
+    covo_flow_cfg cfg;
+    covo::DeviceInfo di;
+    covo::Weights w;
+    // weight views
+    covo::Tensor null_cond, time_w, time_lin_w, time_lin_b, emb_table, embed_wx, embed_wpc, embed_b, conv_wT, conv_b, inv_freq,
+        gb_w, gb_b, final_gamma, pred_w;
+    std::vector<covo::FlowLayerW> layers;
+    int kpc = 0;      // padded width of [emb | cond]
+    int ldx = 0;      // padded width of the x operand (dim_x -> multiple of 64)
+    int npred = 0;    // padded rows of to_pred
+    std::vector<covo::FlowPlan*> plans;
+    cudaStream_t capture_stream = nullptr;
+    bool use_graph = true;
+    bool naive_attn = false;
+};
+
+namespace covo {
+
+inline int flow_bind_weights(covo_flow* h) {
+    const covo_flow_cfg& c = h->cfg;
+    const Weights& w = h->w;
+    COVO_TRY(w.get("null_cond", DT_F32, &h->null_cond));
+    COVO_TRY(w.get("time.w", DT_F32, &h->time_w));
+    COVO_TRY(w.get("time.lin.w", DT_F32, &h->time_lin_w));
+    COVO_TRY(w.get("time.lin.b", DT_F32, &h->time_lin_b));
+    COVO_TRY(w.get("emb.table", DT_F32, &h->emb_table));
+    COVO_TRY(w.get("embed.wx", DT_BF16, &h->embed_wx));
+    COVO_TRY(w.get("embed.wpc", DT_BF16, &h->embed_wpc));
+    COVO_TRY(w.get("embed.b", DT_F32, &h->embed_b));
+    COVO_TRY(w.get("convpos.wT", DT_F32, &h->conv_wT));
+    COVO_TRY(w.get("convpos.b", DT_F32, &h->conv_b));
+    COVO_TRY(w.get("rope.inv_freq", DT_F32, &h->inv_freq));
+    COVO_TRY(w.get("adaln.w", DT_F32, &h->gb_w));
+    COVO_TRY(w.get("adaln.b", DT_F32, &h->gb_b));
+    COVO_TRY(w.get("final.gamma", DT_F32, &h->final_gamma));
+    COVO_TRY(w.get("pred.w", DT_BF16, &h->pred_w));
+    h->ldx = static_cast<int>(h->embed_wx.shape[1]);
+    h->kpc = static_cast<int>(h->embed_wpc.shape[1]);
+    h->npred = static_cast<int>(h->pred_w.shape[0]);
+    if (h->ldx % 64 || h->kpc % 64 || h->npred % 64 || h->ldx < c.dim_x ||
+        h->kpc < c.n_streams * c.dim_phoneme_emb + c.dim_in)
+        return fail(COVO_ERR_WEIGHTS, "packed embed/pred weights have unexpected padding (%d, %d, %d)", h->ldx, h->kpc, h->npred);
+    h->layers.resize(c.depth);
+    for (int L = 0; L < c.depth; ++L) {
+        FlowLayerW& lw = h->layers[L];
+        const std::string p = "L" + std::to_string(L) + ".";
+        if (L >= c.depth / 2) {
+            COVO_TRY(w.get(p + "skip.w", DT_BF16, &lw.skip_w));
+            COVO_TRY(w.get(p + "skip.b", DT_F32, &lw.skip_b));
+        }
+        COVO_TRY(w.get(p + "qkv.w", DT_BF16, &lw.qkv_w));
+        COVO_TRY(w.get(p + "out.w", DT_BF16, &lw.out_w));
+        COVO_TRY(w.get(p + "ff1.w", DT_BF16, &lw.ff1_w));
+        COVO_TRY(w.get(p + "ff1.b", DT_F32, &lw.ff1_b));
+        COVO_TRY(w.get(p + "ff2.w", DT_BF16, &lw.ff2_w));
+        COVO_TRY(w.get(p + "ff2.b", DT_F32, &lw.ff2_b));
+    }
+    return COVO_OK;
+}
+
+inline int flow_num_times(int method, int n_steps) { return method == COVO_ODE_MIDPOINT ? 2 * n_steps : n_steps; }
+
+// Lays the plan's buffers out in the workspace (p.ws may be null: size query only).  Returns bytes used.
+inline size_t flow_layout(const covo_flow* h, FlowPlan& p) {
+    const covo_flow_cfg& c = h->cfg;
+    const int D = c.dim, inner = c.heads * c.dim_head, M = p.M, BN = p.BN;
+    Arena a(p.ws, static_cast<size_t>(-1));
+    p.ids = a.take<long long>(static_cast<size_t>(BN) * c.n_streams);
+    p.cond = a.take<float>(static_cast<size_t>(BN) * c.dim_in);
+    p.x_state = a.take<float>(static_cast<size_t>(BN) * c.dim_x);
+    p.x_in = a.take<float>(static_cast<size_t>(BN) * c.dim_x);
+    p.v_out = a.take<float>(static_cast<size_t>(BN) * c.dim_x);
+    p.d_times = a.take<float>(FLOW_MAX_TIMES);
+    p.tfeat = a.take<float>(static_cast<size_t>(p.n_t) * D);
+    p.temb = a.take<float>(static_cast<size_t>(p.n_t) * D * 4);
+    p.gb = a.take<float>(static_cast<size_t>(p.n_t) * c.depth * 4 * D);
+    p.rope = a.take<float2>(static_cast<size_t>(p.N) * 32);
+    p.a_pc = a.take<__nv_bfloat16>(static_cast<size_t>(M) * h->kpc);
+    p.xin = a.take<__nv_bfloat16>(static_cast<size_t>(M) * h->ldx);
+    p.slots = a.take<__nv_bfloat16>(static_cast<size_t>(c.depth / 2 + 1) * M * D);
+    p.a_norm = a.take<__nv_bfloat16>(static_cast<size_t>(M) * D);
+    p.qkv = a.take<__nv_bfloat16>(static_cast<size_t>(M) * 3 * inner);
+    p.attn_o = a.take<__nv_bfloat16>(static_cast<size_t>(M) * inner);
+    p.ffh = a.take<__nv_bfloat16>(static_cast<size_t>(M) * D * c.ff_mult);
+    p.e_const = a.take<float>(static_cast<size_t>(M) * D);
+    p.h0 = a.take<float>(static_cast<size_t>(M) * D);
+    p.x = a.take<float>(static_cast<size_t>(M) * D);
+    p.vpred = a.take<float>(static_cast<size_t>(M) * c.dim_x);
+    return align_up(a.off, 256);
+}
+
+inline void flow_times(FlowPlan& p) {
+    // torchdiffeq fixed grid: grid[k] = k*h (+t0 = 0), last point snapped to 1; dt = grid[k+1]-grid[k];
+    // midpoint evaluates at grid[k] and grid[k] + dt/2.  All in fp32 like the reference.
+    const float hstep = 1.0f / static_cast<float>(p.n_steps);
+    int idx = 0;
+    for (int k = 0; k < p.n_steps; ++k) {
+        const float t0 = static_cast<float>(k) * hstep;
+        const float t1 = (k + 1 == p.n_steps) ? 1.0f : static_cast<float>(k + 1) * hstep;
+        const float dt = t1 - t0;
+        p.times[idx] = t0;
+        p.dts[idx] = dt;
+        ++idx;
+        if (p.method == COVO_ODE_MIDPOINT) {
+            p.times[idx] = t0 + 0.5f * dt;
+            p.dts[idx] = dt;
+            ++idx;
+        }
+    }
+}
+
+inline ASource a2d(const void* ptr, int K, int rows) {
+    ASource a;
+    a.ptr = ptr;
+    a.K = K;
+    a.rows = rows;
+    a.Z = 1;
+    a.row_stride = K;
+    a.z_stride = static_cast<long long>(K) * rows;
+    return a;
+}
+
+inline void plain_out(GemmArgs& g, int rows, int n_valid, long long ld) {
+    g.n_valid = n_valid;
+    g.out_zs = 0;
+    g.out_rs = ld;
+    g.out_off = 0;
+    g.t_out = rows;
+}
+
+inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
+    const covo_flow_cfg& c = h->cfg;
+    const int D = c.dim, inner = c.heads * c.dim_head, M = p.M, half = c.depth / 2;
+    // per-call constant part of to_embed:  e_const = [emb | cond] W_pc^T + b
+    gemm_defaults(p.op_const.args);
+    COVO_TRY(build_gemm(p.op_const, h->di, a2d(p.a_pc, h->kpc, M), M, 1, h->embed_wpc.ptr, D, 1, 0));
+    plain_out(p.op_const.args, M, D, D);
+    p.op_const.args.bias = h->embed_b.as<float>();
+    p.op_const.args.out_f32 = p.e_const;
+    // per-evaluation part: h0 = x W_x^T + e_const
+    gemm_defaults(p.op_embed.args);
+    COVO_TRY(build_gemm(p.op_embed, h->di, a2d(p.xin, h->ldx, M), M, 1, h->embed_wx.ptr, D, 1, 0));
+    plain_out(p.op_embed.args, M, D, D);
+    p.op_embed.args.residual = p.e_const;
+    p.op_embed.args.out_f32 = p.h0;
+
+    p.op_skip.assign(c.depth, GemmOp());
+    p.op_qkv.assign(c.depth, GemmOp());
+    p.op_out.assign(c.depth, GemmOp());
+    p.op_ff1.assign(c.depth, GemmOp());
+    p.op_ff2.assign(c.depth, GemmOp());
+    for (int L = 0; L < c.depth; ++L) {
+        const FlowLayerW& lw = h->layers[L];
+        if (L >= half) {
+            // x = Linear(cat(x, skip)): two taps over the bf16 slot tensor [slots][M][D]
+            GemmOp& op = p.op_skip[L];
+            gemm_defaults(op.args);
+            ASource a;
+            a.ptr = p.slots;
+            a.K = D;
+            a.rows = M;
+            a.Z = half + 1;
+            a.row_stride = D;
+            a.z_stride = static_cast<long long>(M) * D;
+            COVO_TRY(build_gemm(op, h->di, a, M, 1, lw.skip_w.ptr, D, 2, 0));
+            op.args.tap_row[0] = op.args.tap_row[1] = 0;
+            op.args.tap_z[0] = half;                    // current x
+            op.args.tap_z[1] = c.depth - 1 - L;         // LIFO pop (acoustic.py:306-310)
+            plain_out(op.args, M, D, D);
+            op.args.bias = lw.skip_b.as<float>();
+            op.args.out_f32 = p.x;
+        }
+        {
+            GemmOp& op = p.op_qkv[L];
+            gemm_defaults(op.args);
+            COVO_TRY(build_gemm(op, h->di, a2d(p.a_norm, D, M), M, 1, lw.qkv_w.ptr, 3 * inner, 1, 0));
+            plain_out(op.args, M, 3 * inner, 3 * inner);
+            op.args.out_h = p.qkv;
+            op.args.rope = p.rope;
+            op.args.rope_seq = p.N;
+            op.args.rope_cols = 2 * inner;
+        }
+        {
+            GemmOp& op = p.op_out[L];
+            gemm_defaults(op.args);
+            COVO_TRY(build_gemm(op, h->di, a2d(p.attn_o, inner, M), M, 1, lw.out_w.ptr, D, 1, 0));
+            plain_out(op.args, M, D, D);
+            op.args.residual = p.x;
+            op.args.out_f32 = p.x;
+        }
+        {
+            GemmOp& op = p.op_ff1[L];
+            gemm_defaults(op.args);
+            COVO_TRY(build_gemm(op, h->di, a2d(p.a_norm, D, M), M, 1, lw.ff1_w.ptr, D * c.ff_mult, 1, 0));
+            plain_out(op.args, M, D * c.ff_mult, D * c.ff_mult);
+            op.args.bias = lw.ff1_b.as<float>();
+            op.args.out_h = p.ffh;
+            op.args.act_h = ACT_GELU;
+        }
+        {
+            GemmOp& op = p.op_ff2[L];
+            gemm_defaults(op.args);
+            COVO_TRY(build_gemm(op, h->di, a2d(p.ffh, D * c.ff_mult, M), M, 1, lw.ff2_w.ptr, D, 1, 0));
+            plain_out(op.args, M, D, D);
+            op.args.bias = lw.ff2_b.as<float>();
+            op.args.residual = p.x;
+            op.args.out_f32 = p.x;
+            // bf16 copy of the next layer's input: a skip slot (first half) or the "current" slot (second half)
+            if (L + 1 < c.depth) {
+                const int slot = (L + 1 < half) ? (L + 1) : half;
+                op.args.out_h = p.slots + static_cast<size_t>(slot) * M * D;
+            }
+        }
+    }
+    gemm_defaults(p.op_pred.args);
+    COVO_TRY(build_gemm(p.op_pred, h->di, a2d(p.a_norm, D, M), M, 1, h->pred_w.ptr, h->npred, 1, 0));
+    plain_out(p.op_pred.args, M, c.dim_x, c.dim_x);
+    p.op_pred.args.out_f32 = p.vpred;
+
+    // attention
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(3 * inner), static_cast<uint64_t>(p.N), static_cast<uint64_t>(M / p.N)};
+        uint64_t str[2] = {static_cast<uint64_t>(3 * inner) * 2, static_cast<uint64_t>(3 * inner) * 2 * p.N};
+        uint32_t box[3] = {64, 128, 1};
+        COVO_TRY(make_tmap(&p.attn.tmQKV, p.qkv, 3, dims, str, box, 0));
+        p.attn.out = p.attn_o;
+        p.attn.N = p.N;
+        p.attn.heads = c.heads;
+        p.attn.inner = inner;
+        p.attn.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(c.dim_head));
+    }
+    return COVO_OK;
+}
+
+inline int launch_attention(const covo_flow* h, const FlowPlan& p, cudaStream_t st) {
+    const int Bt = p.M / p.N;
+    if (h->naive_attn) {
+        dim3 grid(ceil_div(p.N, 8), h->cfg.heads, Bt);
+        naive_attention_kernel<<<grid, 256, 0, st>>>(p.qkv, p.attn_o, p.N, h->cfg.heads, p.attn.inner,
+                                                     1.0f / sqrtf(static_cast<float>(h->cfg.dim_head)));
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            COVO_CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+            attr = true;
+        }
+        dim3 grid(ceil_div(p.N, ATT_BM), h->cfg.heads, Bt);
+        attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(p.attn);
+    }
+    COVO_CK(cudaGetLastError());
+    return COVO_OK;
+}
+
+template <int V>
+inline void launch_rmsnorm_v(const float* x, const float* g, const float* b, __nv_bfloat16* out, int M, cudaStream_t st) {
+    rmsnorm_kernel<V><<<ceil_div(M, 8), 256, 0, st>>>(x, g, b, out, M);
+}
+inline int launch_rmsnorm(const float* x, const float* g, const float* b, __nv_bfloat16* out, int M, int D, cudaStream_t st) {
+    switch (D / 128) {
+        case 8: launch_rmsnorm_v<8>(x, g, b, out, M, st); break;
+        case 4: launch_rmsnorm_v<4>(x, g, b, out, M, st); break;
+        case 2: launch_rmsnorm_v<2>(x, g, b, out, M, st); break;
+        case 1: launch_rmsnorm_v<1>(x, g, b, out, M, st); break;
+        default: return fail(COVO_ERR_INVALID, "dim %d unsupported by rmsnorm (need 128/256/512/1024)", D);
+    }
+    COVO_CK(cudaGetLastError());
+    return COVO_OK;
+}
+
+// Work that depends on the call's inputs but not on the ODE state: time tables, RoPE table, e_const.
+inline int flow_enqueue_prologue(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
+    const covo_flow_cfg& c = h->cfg;
+    const int D = c.dim;
+    TimesArg ta;
+    memcpy(ta.t, p.times, sizeof(float) * p.n_t);
+    set_times_kernel<<<1, FLOW_MAX_TIMES, 0, st>>>(p.d_times, ta, p.n_t);
+    time_features_kernel<<<p.n_t, 256, 0, st>>>(p.d_times, h->time_w.as<float>(), p.tfeat, p.n_t, D / 2);
+    {
+        dim3 g(ceil_div(4 * D, 64), ceil_div(p.n_t, 64));
+        sgemm_nt_kernel<<<g, 256, 0, st>>>(p.tfeat, h->time_lin_w.as<float>(), h->time_lin_b.as<float>(), p.temb, p.n_t, 4 * D,
+                                           D, SG_SILU);
+    }
+    {
+        const int NO = c.depth * 4 * D;       // per layer: gamma1 | beta1 | gamma2 | beta2
+        dim3 g(ceil_div(NO, 64), ceil_div(p.n_t, 64));
+        sgemm_nt_kernel<<<g, 256, 0, st>>>(p.temb, h->gb_w.as<float>(), h->gb_b.as<float>(), p.gb, p.n_t, NO, 4 * D, SG_NONE);
+    }
+    rope_table_kernel<<<ceil_div(p.N * 32, 256), 256, 0, st>>>(h->inv_freq.as<float>(), p.rope, p.N, 32);
+    embed_input_kernel<<<p.M, 256, 0, st>>>(p.ids, p.cond, h->emb_table.as<float>(), h->null_cond.as<float>(), p.a_pc, p.BN,
+                                            c.n_streams, c.dim_phoneme_emb, c.dim_in, c.num_phoneme_tokens, h->kpc);
+    COVO_CK(cudaGetLastError());
+    COVO_TRY(launch_gemm(p.op_const, st));
+    *launches += 7;
+    return COVO_OK;
+}
+
+// One network pass over both CFG branches: xin (bf16 state) -> vpred [M, dim_x].
+inline int flow_enqueue_network(covo_flow* h, FlowPlan& p, int t_idx, cudaStream_t st, int* launches) {
+    const covo_flow_cfg& c = h->cfg;
+    const int D = c.dim, M = p.M, half = c.depth / 2;
+    const int Bt = M / p.N;
+    COVO_TRY(launch_gemm(p.op_embed, st));
+    {
+        dim3 g(ceil_div(D, 256), ceil_div(p.N, 8), Bt);
+        convpos_kernel<31, 8><<<g, 256, 0, st>>>(p.h0, h->conv_wT.as<float>(), h->conv_b.as<float>(), p.x, p.slots, p.N, D);
+        COVO_CK(cudaGetLastError());
+    }
+    *launches += 2;
+    const float* gb_t = p.gb + static_cast<size_t>(t_idx) * c.depth * 4 * D;
+    for (int L = 0; L < c.depth; ++L) {
+        const float* gbl = gb_t + static_cast<size_t>(L) * 4 * D;
+        if (L >= half) {
+            COVO_TRY(launch_gemm(p.op_skip[L], st));
+            ++*launches;
+        }
+        COVO_TRY(launch_rmsnorm(p.x, gbl, gbl + D, p.a_norm, M, D, st));
+        COVO_TRY(launch_gemm(p.op_qkv[L], st));
+        COVO_TRY(launch_attention(h, p, st));
+        COVO_TRY(launch_gemm(p.op_out[L], st));
+        COVO_TRY(launch_rmsnorm(p.x, gbl + 2 * D, gbl + 3 * D, p.a_norm, M, D, st));
+        COVO_TRY(launch_gemm(p.op_ff1[L], st));
+        COVO_TRY(launch_gemm(p.op_ff2[L], st));
+        *launches += 7;
+    }
+    COVO_TRY(launch_rmsnorm(p.x, h->final_gamma.as<float>(), nullptr, p.a_norm, M, D, st));
+    COVO_TRY(launch_gemm(p.op_pred, st));
+    *launches += 2;
+    return COVO_OK;
+}
+
+inline int flow_enqueue_sample(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
+    const covo_flow_cfg& c = h->cfg;
+    const int n_el = p.BN * c.dim_x;
+    const int eb = ceil_div(n_el, 256);
+    COVO_TRY(flow_enqueue_prologue(h, p, st, launches));
+    state_to_input_kernel<<<eb, 256, 0, st>>>(p.x_state, p.xin, p.BN, c.dim_x, h->ldx, p.two_branch);
+    ++*launches;
+    int ti = 0;
+    for (int k = 0; k < p.n_steps; ++k) {
+        if (p.method == COVO_ODE_MIDPOINT) {
+            const float dt = p.dts[ti];
+            COVO_TRY(flow_enqueue_network(h, p, ti, st, launches));
+            // y_mid = y0 + f0 * dt/2 -> network input only
+            cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, nullptr, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
+                                                  p.cond_scale, 0.5f * dt, p.two_branch);
+            ++ti;
+            COVO_TRY(flow_enqueue_network(h, p, ti, st, launches));
+            // y1 = y0 + dt * f(t0 + dt/2, y_mid)
+            cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, p.x_state, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
+                                                  p.cond_scale, dt, p.two_branch);
+            ++ti;
+            *launches += 2;
+        } else {
+            const float dt = p.dts[ti];
+            COVO_TRY(flow_enqueue_network(h, p, ti, st, launches));
+            cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, p.x_state, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
+                                                  p.cond_scale, dt, p.two_branch);
+            ++ti;
+            ++*launches;
+        }
+    }
+    COVO_CK(cudaGetLastError());
+    return COVO_OK;
+}
+
+inline int flow_enqueue_velocity(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
+    const covo_flow_cfg& c = h->cfg;
+    const int n_el = p.BN * c.dim_x;
+    const int eb = ceil_div(n_el, 256);
+    COVO_TRY(flow_enqueue_prologue(h, p, st, launches));
+    state_to_input_kernel<<<eb, 256, 0, st>>>(p.x_in, p.xin, p.BN, c.dim_x, h->ldx, p.two_branch);
+    COVO_TRY(flow_enqueue_network(h, p, 0, st, launches));
+    cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, nullptr, nullptr, p.v_out, nullptr, p.BN, c.dim_x, h->ldx, p.cond_scale,
+                                          0.f, p.two_branch);
+    COVO_CK(cudaGetLastError());
+    *launches += 2;
+    return COVO_OK;
+}
+
+inline void flow_free_plan(FlowPlan* p) {
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    delete p;
+}
+
+// Finds or builds the plan for this call shape.  single_eval: covo_flow_velocity (no graph; t varies per call).
+inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, float cond_scale, int single_eval, void* ws,
+                         size_t ws_bytes, FlowPlan** out) {
+    const covo_flow_cfg& c = h->cfg;
+    if (B < 1 || N < 1) return fail(COVO_ERR_INVALID, "B=%d N=%d must be positive", B, N);
+    if (method != COVO_ODE_EULER && method != COVO_ODE_MIDPOINT) return fail(COVO_ERR_INVALID, "unknown ODE method %d", method);
+    const int n_t = single_eval ? 1 : flow_num_times(method, n_steps);
+    if (n_steps < 1 || n_t > FLOW_MAX_TIMES) return fail(COVO_ERR_INVALID, "n_steps=%d out of range", n_steps);
+    for (FlowPlan* q : h->plans) {
+        if (q->B == B && q->N == N && q->method == method && q->n_steps == n_steps && q->cond_scale == cond_scale &&
+            q->single_eval == single_eval && q->ws == ws) {
+            *out = q;
+            return COVO_OK;
+        }
+    }
+    FlowPlan* p = new FlowPlan();
+    p->B = B;
+    p->N = N;
+    p->method = method;
+    p->n_steps = n_steps;
+    p->cond_scale = cond_scale;
+    p->single_eval = single_eval;
+    p->ws = ws;
+    p->two_branch = (cond_scale != 1.0f) ? 1 : 0;     // acoustic.py:423-424: cond_scale == 1 returns the cond branch only
+    p->BN = B * N;
+    p->M = p->BN * (p->two_branch ? 2 : 1);
+    p->n_t = n_t;
+    if (!single_eval) flow_times(*p);
+    const size_t need = flow_layout(h, *p);
+    if (need > ws_bytes || ws == nullptr) {
+        delete p;
+        return fail(COVO_ERR_INVALID, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    }
+    int rc = flow_build_ops(h, *p);
+    if (rc != COVO_OK) {
+        delete p;
+        return rc;
+    }
+    // padding columns of the bf16 operands must be zero (they meet zero weight columns, but 0 * NaN != 0)
+    cudaMemsetAsync(p->a_pc, 0, static_cast<size_t>(p->M) * h->kpc * 2, h->capture_stream);
+    cudaMemsetAsync(p->xin, 0, static_cast<size_t>(p->M) * h->ldx * 2, h->capture_stream);
+    COVO_CK(cudaStreamSynchronize(h->capture_stream));
+    if (!single_eval && h->use_graph) {
+        cudaGraph_t graph = nullptr;
+        int launches = 0;
+        COVO_CK(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+        rc = flow_enqueue_sample(h, *p, h->capture_stream, &launches);
+        cudaError_t e = cudaStreamEndCapture(h->capture_stream, &graph);
+        if (rc != COVO_OK || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            delete p;
+            return rc != COVO_OK ? rc : fail(COVO_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+        }
+        e = cudaGraphInstantiate(&p->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            delete p;
+            return fail(COVO_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        }
+        p->launches = launches;
+    }
+    if (h->plans.size() >= 8) {
+        flow_free_plan(h->plans.front());
+        h->plans.erase(h->plans.begin());
+    }
+    h->plans.push_back(p);
+    *out = p;
+    return COVO_OK;
+}
+
+}  // namespace covo

@@ -1,0 +1,289 @@
+// HiFi-GAN generator: host-side plan for Generator.forward (hifi-gan/models.py:100-116).
+// Activations are time-major [B, T, C_pad] (channels contiguous, padded to a multiple of 64 with zeros),
+// 16-bit (bf16 or fp16) as MMA operands plus an fp32 residual stream.  Every conv is one launch of the
+// tcgen05 implicit-GEMM kernel (gemm_sm100.cuh) with LeakyReLU / bias / residual fused in its epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace covo {
+
+struct HifiStage {
+    int c_in_pad, c_out_pad, c_out;
+    int t_in, t_out;
+    int stride, ksize, pad, jtaps;
+    float* x = nullptr;            // fp32 [B, t_out, c_out_pad] : ConvTranspose1d output (residual start)
+    uint16_t* a0 = nullptr;        // 16-bit lrelu(x)
+    float* xr[4] = {nullptr, nullptr, nullptr, nullptr};      // per-resblock fp32 stream
+    uint16_t* ar[4] = {nullptr, nullptr, nullptr, nullptr};   // lrelu(xr)
+    uint16_t* hr[4] = {nullptr, nullptr, nullptr, nullptr};   // lrelu(conv1 out)
+    uint16_t* out_act = nullptr;   // lrelu(mean of resblocks): input of the next stage / conv_post
+    GemmOp up;
+    std::vector<GemmOp> convs;     // in launch order
+};
+
+struct HifiPlan {
+    int B = 0, T = 0;
+    void* ws = nullptr;
+    uint16_t* mel_tc = nullptr;    // [B, T, mel_pad]
+    uint16_t* pre_act = nullptr;   // lrelu(conv_pre) [B, T, c0_pad]
+    GemmOp pre;
+    std::vector<HifiStage> stages;
+    int launches = 0;
+};
+
+}  // namespace covo
+
+struct covo_hifigan {
+    covo_hifigan_cfg cfg;
+    covo::DeviceInfo di;
+    covo::Weights w;
+    int mel_pad = 0;
+    int is_fp16 = 0;
+    std::vector<covo::HifiPlan*> plans;
+};
+
+namespace covo {
+
+inline int hifi_chan(const covo_hifigan_cfg& c, int stage /* -1: conv_pre output */) {
+    return c.upsample_initial_channel >> (stage + 1);
+}
+inline int pad64(int c) { return round_up(c, 64); }
+
+inline int64_t hifi_out_len(const covo_hifigan_cfg& c, int T) {
+    int64_t L = T;
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i], p = (k - u) / 2;
+        L = (L - 1) * u - 2 * p + k;
+    }
+    return L;
+}
+
+inline size_t hifi_layout(const covo_hifigan* h, HifiPlan& p) {
+    const covo_hifigan_cfg& c = h->cfg;
+    Arena a(p.ws, static_cast<size_t>(-1));
+    const size_t B = p.B;
+    p.mel_tc = a.take<uint16_t>(B * p.T * h->mel_pad);
+    p.pre_act = a.take<uint16_t>(B * p.T * pad64(hifi_chan(c, -1)));
+    p.stages.assign(c.num_upsamples, HifiStage());
+    int t = p.T;
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        HifiStage& s = p.stages[i];
+        s.stride = c.upsample_rates[i];
+        s.ksize = c.upsample_kernel_sizes[i];
+        s.pad = (s.ksize - s.stride) / 2;
+        s.jtaps = ceil_div(s.ksize, s.stride);
+        s.c_in_pad = pad64(hifi_chan(c, i - 1));
+        s.c_out = hifi_chan(c, i);
+        s.c_out_pad = pad64(s.c_out);
+        s.t_in = t;
+        s.t_out = (t - 1) * s.stride - 2 * s.pad + s.ksize;
+        t = s.t_out;
+        const size_t n = B * s.t_out * s.c_out_pad;
+        s.x = a.take<float>(n);
+        s.a0 = a.take<uint16_t>(n);
+        for (int j = 0; j < c.num_kernels; ++j) {
+            s.xr[j] = a.take<float>(n);
+            s.ar[j] = a.take<uint16_t>(n);
+            s.hr[j] = a.take<uint16_t>(n);
+        }
+        s.out_act = a.take<uint16_t>(n);
+    }
+    return align_up(a.off, 256);
+}
+
+inline ASource a3d(const void* ptr, int C, int T, int B) {
+    ASource a;
+    a.ptr = ptr;
+    a.K = C;
+    a.rows = T;
+    a.Z = B;
+    a.row_stride = C;
+    a.z_stride = static_cast<long long>(C) * T;
+    return a;
+}
+
+// Conv1d(C->C_out, k, dilation d, "same" padding) as taps over time-major activations.
+inline int hifi_conv_op(const covo_hifigan* h, GemmOp& op, const void* act, int c_in_pad, int T, int B, const Tensor& w,
+                        const Tensor& bias, int c_out_pad, int k, int dil) {
+    gemm_defaults(op.args);
+    COVO_TRY(build_gemm(op, h->di, a3d(act, c_in_pad, T, B), T, B, w.ptr, c_out_pad, k, h->is_fp16));
+    const int pad = (k * dil - dil) / 2;                       // get_padding, hifi-gan/utils.py:34-35
+    for (int j = 0; j < k; ++j) {
+        op.args.tap_row[j] = j * dil - pad;
+        op.args.tap_z[j] = 0;
+    }
+    op.args.n_valid = c_out_pad;
+    op.args.out_zs = static_cast<long long>(T) * c_out_pad;
+    op.args.out_rs = c_out_pad;
+    op.args.t_out = T;
+    op.args.bias = bias.as<float>();
+    op.args.h_is_fp16 = h->is_fp16;
+    return COVO_OK;
+}
+
+inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
+    const covo_hifigan_cfg& c = h->cfg;
+    const Weights& w = h->w;
+    const uint32_t hdt = h->is_fp16 ? DT_F16 : DT_BF16;
+    Tensor tw, tb;
+    COVO_TRY(w.get("conv_pre.w", hdt, &tw));
+    COVO_TRY(w.get("conv_pre.b", DT_F32, &tb));
+    const int c0p = pad64(hifi_chan(c, -1));
+    COVO_TRY(hifi_conv_op(h, p.pre, p.mel_tc, h->mel_pad, p.T, p.B, tw, tb, c0p, 7, 1));
+    p.pre.args.out_h = p.pre_act;                               // x = lrelu(conv_pre(mel)) (models.py:101-103)
+    p.pre.args.act_h = ACT_LRELU;
+    p.pre.args.slope = 0.1f;
+    p.launches = 2;                                             // mel transpose + conv_pre
+
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        HifiStage& s = p.stages[i];
+        const void* in_act = (i == 0) ? p.pre_act : p.stages[i - 1].out_act;
+        // ---- ConvTranspose1d, polyphase: output sample o = stride*q + r - pad, phase r in [0, stride);
+        //      D[q, r*C + co] = sum_j x[q - j] W[:, co, r + stride*j]   (weights packed [stride*C_pad, jtaps*Cin_pad])
+        {
+            const std::string nm = "ups." + std::to_string(i);
+            COVO_TRY(w.get(nm + ".w", hdt, &tw));
+            COVO_TRY(w.get(nm + ".b", DT_F32, &tb));
+            GemmOp& op = s.up;
+            gemm_defaults(op.args);
+            COVO_TRY(build_gemm(op, h->di, a3d(in_act, s.c_in_pad, s.t_in, p.B), s.t_in + s.jtaps - 1, p.B, tw.ptr,
+                                s.stride * s.c_out_pad, s.jtaps, h->is_fp16));
+            for (int j = 0; j < s.jtaps; ++j) {
+                op.args.tap_row[j] = -j;
+                op.args.tap_z[j] = 0;
+            }
+            op.args.n_valid = s.stride * s.c_out_pad;
+            op.args.out_zs = static_cast<long long>(s.t_out) * s.c_out_pad;
+            op.args.out_rs = static_cast<long long>(s.stride) * s.c_out_pad;
+            op.args.out_off = -static_cast<long long>(s.pad) * s.c_out_pad;
+            op.args.up_s = s.stride;
+            op.args.up_p = s.pad;
+            op.args.phase_w = s.c_out_pad;
+            op.args.t_out = s.t_out;
+            op.args.bias = tb.as<float>();
+            op.args.out_f32 = s.x;
+            op.args.out_h = s.a0;
+            op.args.act_h = ACT_LRELU;
+            op.args.slope = 0.1f;
+            op.args.h_is_fp16 = h->is_fp16;
+            ++p.launches;
+        }
+        // ---- resblocks
+        s.convs.clear();
+        for (int j = 0; j < c.num_kernels; ++j) {
+            const int k = c.resblock_kernel_sizes[j];
+            const int r = i * c.num_kernels + j;
+            for (int m = 0; m < c.num_dilations; ++m) {
+                const int d = c.resblock_dilations[j][m];
+                const void* in1 = (m == 0) ? s.a0 : s.ar[j];
+                const float* res = (m == 0) ? s.x : s.xr[j];
+                if (c.resblock_type == 1) {
+                    // xt = c2(lrelu(c1(lrelu(x)))); x = xt + x     (models.py:35-42)
+                    const std::string n1 = "rb." + std::to_string(r) + ".c1." + std::to_string(m);
+                    const std::string n2 = "rb." + std::to_string(r) + ".c2." + std::to_string(m);
+                    COVO_TRY(w.get(n1 + ".w", hdt, &tw));
+                    COVO_TRY(w.get(n1 + ".b", DT_F32, &tb));
+                    GemmOp o1;
+                    COVO_TRY(hifi_conv_op(h, o1, in1, s.c_out_pad, s.t_out, p.B, tw, tb, s.c_out_pad, k, d));
+                    o1.args.out_h = s.hr[j];
+                    o1.args.act_h = ACT_LRELU;
+                    s.convs.push_back(o1);
+                    COVO_TRY(w.get(n2 + ".w", hdt, &tw));
+                    COVO_TRY(w.get(n2 + ".b", DT_F32, &tb));
+                    GemmOp o2;
+                    COVO_TRY(hifi_conv_op(h, o2, s.hr[j], s.c_out_pad, s.t_out, p.B, tw, tb, s.c_out_pad, k, 1));
+                    o2.args.residual = res;
+                    o2.args.out_f32 = s.xr[j];
+                    if (m + 1 < c.num_dilations) {
+                        o2.args.out_h = s.ar[j];
+                        o2.args.act_h = ACT_LRELU;
+                    }
+                    s.convs.push_back(o2);
+                } else {
+                    // xt = c(lrelu(x)); x = xt + x                   (models.py:63-68)
+                    const std::string n1 = "rb." + std::to_string(r) + ".c." + std::to_string(m);
+                    COVO_TRY(w.get(n1 + ".w", hdt, &tw));
+                    COVO_TRY(w.get(n1 + ".b", DT_F32, &tb));
+                    GemmOp o1;
+                    COVO_TRY(hifi_conv_op(h, o1, in1, s.c_out_pad, s.t_out, p.B, tw, tb, s.c_out_pad, k, d));
+                    o1.args.residual = res;
+                    o1.args.out_f32 = s.xr[j];
+                    if (m + 1 < c.num_dilations) {
+                        o1.args.out_h = s.ar[j];
+                        o1.args.act_h = ACT_LRELU;
+                    }
+                    s.convs.push_back(o1);
+                }
+            }
+        }
+        p.launches += static_cast<int>(s.convs.size()) + 1;     // + stage mean
+    }
+    p.launches += 1;                                            // conv_post
+    return COVO_OK;
+}
+
+inline int hifi_get_plan(covo_hifigan* h, int B, int T, void* ws, size_t ws_bytes, HifiPlan** out) {
+    if (B < 1 || T < 1) return fail(COVO_ERR_INVALID, "B=%d T=%d must be positive", B, T);
+    for (HifiPlan* q : h->plans)
+        if (q->B == B && q->T == T && q->ws == ws) {
+            *out = q;
+            return COVO_OK;
+        }
+    HifiPlan* p = new HifiPlan();
+    p->B = B;
+    p->T = T;
+    p->ws = ws;
+    const size_t need = hifi_layout(h, *p);
+    if (ws == nullptr || need > ws_bytes) {
+        delete p;
+        return fail(COVO_ERR_INVALID, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    }
+    int rc = hifi_build_ops(h, *p);
+    if (rc != COVO_OK) {
+        delete p;
+        return rc;
+    }
+    // zero once: padded channels of the mel operand must be exact zeros
+    COVO_CK(cudaMemset(p->mel_tc, 0, static_cast<size_t>(B) * T * h->mel_pad * 2));
+    if (h->plans.size() >= 8) {
+        delete h->plans.front();
+        h->plans.erase(h->plans.begin());
+    }
+    h->plans.push_back(p);
+    *out = p;
+    return COVO_OK;
+}
+
+inline int hifi_enqueue(covo_hifigan* h, HifiPlan& p, const float* mel, void* wav, int out_dtype, cudaStream_t st) {
+    const covo_hifigan_cfg& c = h->cfg;
+    {
+        dim3 g(ceil_div(p.T, 32), ceil_div(c.num_mels, 32), p.B);
+        mel_to_tc_kernel<<<g, 256, 0, st>>>(mel, p.mel_tc, c.num_mels, p.T, h->mel_pad, h->is_fp16);
+        COVO_CK(cudaGetLastError());
+    }
+    COVO_TRY(launch_gemm(p.pre, st));
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        HifiStage& s = p.stages[i];
+        COVO_TRY(launch_gemm(s.up, st));
+        for (const GemmOp& op : s.convs) COVO_TRY(launch_gemm(op, st));
+        const size_t n4 = static_cast<size_t>(p.B) * s.t_out * s.c_out_pad / 4;
+        const float slope = (i + 1 == c.num_upsamples) ? 0.01f : 0.1f;     // models.py:103 vs :112 (F.leaky_relu default)
+        stage_mean_act_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
+            s.xr[0], c.num_kernels > 1 ? s.xr[1] : nullptr, c.num_kernels > 2 ? s.xr[2] : nullptr, s.out_act, n4,
+            1.0f / static_cast<float>(c.num_kernels), slope, h->is_fp16);
+        COVO_CK(cudaGetLastError());
+    }
+    {
+        const HifiStage& s = p.stages.back();
+        Tensor tw, tb;
+        COVO_TRY(h->w.get("conv_post.w", DT_F32, &tw));
+        COVO_TRY(h->w.get("conv_post.b", DT_F32, &tb));
+        dim3 g(ceil_div(s.t_out, 256), p.B);
+        conv_post_kernel<<<g, 256, 7 * s.c_out_pad * sizeof(float), st>>>(s.out_act, tw.as<float>(), tb.as<float>(), wav, s.t_out,
+                                                                          s.c_out_pad, s.c_out_pad, h->is_fp16, out_dtype);
+        COVO_CK(cudaGetLastError());
+    }
+    return COVO_OK;
+}
+
+}  // namespace covo

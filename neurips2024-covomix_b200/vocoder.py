@@ -1,0 +1,111 @@
+"""Host-side mirror of the HiFi-GAN ``Generator`` (hifi-gan/models.py:75-125 ==
+covomix/vocoder/models.py) backed by libcovomix_b200.so.  ``gen(mel)`` takes the reference's input
+([80, T] or [B, 80, T] fp32) and returns the reference's output shape ([1, 1, L] / [B, 1, L] fp32,
+L = 160*T + 32 for config_covomix.json); ``eval()`` / ``remove_weight_norm()`` / ``to()`` exist so the
+generation scripts' load sequence (monologue_generation.py:382-386) runs unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _native as nat
+from .packing import pack_hifigan_weights
+from .synthetic import HIFIGAN_COVOMIX, HifiganConfig
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class B200Generator:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: HifiganConfig = HIFIGAN_COVOMIX, device="cuda:0",
+                 h_format: str = "bf16"):
+        self.h = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("covomix_b200 has no CPU path; device must be a CUDA (sm_100) device")
+        nk = len(cfg.resblock_kernel_sizes)
+        nd = len(cfg.resblock_dilation_sizes[0])
+        ccfg = nat.HifiganCfg()
+        ccfg.num_mels = cfg.num_mels
+        ccfg.upsample_initial_channel = cfg.upsample_initial_channel
+        ccfg.num_upsamples = len(cfg.upsample_rates)
+        for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
+            ccfg.upsample_rates[i] = u
+            ccfg.upsample_kernel_sizes[i] = k
+        ccfg.num_kernels = nk
+        ccfg.num_dilations = nd
+        for j in range(nk):
+            ccfg.resblock_kernel_sizes[j] = cfg.resblock_kernel_sizes[j]
+            for m in range(nd):
+                ccfg.resblock_dilations[j][m] = cfg.resblock_dilation_sizes[j][m]
+        ccfg.resblock_type = int(cfg.resblock)
+        ccfg.h_format = nat.COVO_H_FP16 if h_format == "fp16" else nat.COVO_H_BF16
+        blob = pack_hifigan_weights(state_dict, cfg, h_format)
+        self._h = C.c_void_p()
+        nat.check(nat.lib().covo_hifigan_create(C.byref(ccfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
+                                                self.device.index or 0, C.byref(self._h)), "covo_hifigan_create")
+        self._ws: Dict[tuple, torch.Tensor] = {}
+
+    # reference-API no-ops (weights are already folded / on device)
+    def eval(self):
+        return self
+
+    def remove_weight_norm(self):
+        return None
+
+    def to(self, device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("covomix_b200 has no CPU path")
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            nat.lib().covo_hifigan_destroy(self._h)
+            self._h = C.c_void_p()
+        self._ws = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def out_len(self, T: int) -> int:
+        return int(nat.lib().covo_hifigan_out_len(self._h, T))
+
+    def launches_per_forward(self) -> int:
+        return nat.lib().covo_hifigan_launches_per_forward(self._h)
+
+    def _workspace(self, B: int, T: int) -> torch.Tensor:
+        key = (B, T)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = nat.lib().covo_hifigan_workspace_bytes(self._h, B, T)
+            if len(self._ws) >= 4:
+                self._ws.pop(next(iter(self._ws)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    @torch.inference_mode()
+    def forward(self, mel: torch.Tensor, out_dtype: str = "f32") -> torch.Tensor:
+        x = mel if mel.ndim == 3 else mel[None]
+        if x.ndim != 3 or x.shape[1] != self.h.num_mels:
+            raise ValueError(f"mel must be [{self.h.num_mels}, T] or [B, {self.h.num_mels}, T], got {tuple(mel.shape)}")
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        B, _, T = x.shape
+        L = self.out_len(T)
+        code, tdt = {"f32": (nat.COVO_WAV_F32, torch.float32), "f16": (nat.COVO_WAV_F16, torch.float16),
+                     "i16": (nat.COVO_WAV_I16, torch.int16)}[out_dtype]
+        wav = torch.empty(B, 1, L, dtype=tdt, device=self.device)
+        ws = self._workspace(B, T)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib().covo_hifigan_forward(self._h, _ptr(x), _ptr(wav), B, T, code, _ptr(ws), ws.numel(),
+                                                 C.c_void_p(stream)), "covo_hifigan_forward")
+        return wav
+
+    __call__ = forward
