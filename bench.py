@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds/second of the CoVoMix inference hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+    workload c3 (default; BASELINE.json configs[2], the config the metric is quoted on):
+        VoMix 2-stream acoustic model, 64 Euler flow-matching steps (64 NFE x 2 CFG passes),
+        B = 8 dialogues of 30 s (N = 1650 frames = 150 prompt + 1500 generated), cond_scale 0.7,
+        followed by the HiFi-GAN generator on the 8 x [80, 1500] generated mels -> 8 x 240032 samples.
+    workload c2: VoSingle, 32 Euler steps, 10 s monologue (N = 650), B = 1, + vocoder.
+value = B * 30 s * n_gpus / seconds-per-step (whole job, inputs resident in HBM).
+e2e   = the same through the public Python API with pinned HOST inputs and a device->host read of the waveform.
+
+--impl reference times the reference algorithm's CPU implementation (the fp32 PyTorch oracle port,
+oracle/covomix_oracle.py; the reference itself is Python and /root/reference does not travel) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FRAME_RATE = 50.0
+WORKLOADS = {
+    "c3": dict(model="vomix", B=8, N=1650, prompt=150, method="euler", n_steps=64,
+               name="C3: VoMix 2-stream, 64 Euler steps (128 network passes), 30 s dialogue, batch 8, + HiFi-GAN"),
+    "c2": dict(model="vosingle", B=1, N=650, prompt=150, method="euler", n_steps=32,
+               name="C2: VoSingle, 32 Euler steps, 10 s monologue, batch 1, + HiFi-GAN"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=p.get("bf16_tflops_sustained", 1409.8), hbm=p.get("hbm_gbs", 6548.8), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        # median over the samples taken under load (upper half; the first samples can predate the launch)
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(wl, device=None, seed=30):
+    from covomix_b200 import synthetic as syn
+    cfg = syn.VOMIX if wl["model"] == "vomix" else syn.VOSINGLE
+    ids, cond, y0, mask = syn.synthetic_flow_inputs(cfg, wl["B"], wl["N"], prompt=wl["prompt"], seed=seed)
+    return cfg, ids, cond, y0, mask
+
+
+def algorithmic_flops(cfg, wl):
+    """per token per pass 2*(L_lin + 16384*N); vocoder 281.3 MFLOP per mel frame."""
+    N, B = wl["N"], wl["B"]
+    inner = cfg.heads * cfg.dim_head
+    lin = cfg.embed_in * cfg.dim + 31 * cfg.dim + cfg.depth * (cfg.dim * 3 * inner + inner * cfg.dim + 2 * cfg.dim * cfg.dim * cfg.ff_mult) \
+        + (cfg.depth // 2) * 2 * cfg.dim * cfg.dim + cfg.dim * cfg.dim_x
+    attn = cfg.depth * 2 * N * inner
+    per_pass = 2.0 * (lin + attn) * N * B
+    nfe = wl["n_steps"] * (2 if wl["method"] == "midpoint" else 1)
+    flow = per_pass * nfe * 2
+    voc = 281.3e6 * (N - wl["prompt"]) * B
+    return flow, voc
+
+
+# ======================================================================================== reference arm (CPU)
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import covomix_b200  # noqa: F401
+    from covomix_b200 import synthetic as syn
+    from oracle import covomix_oracle as orc
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = syn.VOMIX if wl["model"] == "vomix" else syn.VOSINGLE
+    sd = syn.synthetic_flow_state_dict(cfg, 1234)
+    hsd = syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234)
+    # bounded sample: ONE item of the batch, ONE CFG velocity evaluation (2 network passes) + the vocoder on one item;
+    # the full step is B items x n_eval evaluations (+ B vocoder passes) of exactly this work, so seconds-per-step is
+    # extrapolated linearly (the reference processes items one at a time: dialogue_generation.py:283).
+    wl1 = dict(wl, B=1)
+    _, ids, cond, y0, _ = make_inputs(wl1)
+    gen_frames = wl["N"] - wl["prompt"]
+    mel = syn.synthetic_logmel(torch.Generator().manual_seed(31), 1, 80, gen_frames)
+    n_eval = wl["n_steps"] * (2 if wl["method"] == "midpoint" else 1)
+
+    def one():
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            orc.velocity_cfg(sd, cfg, y0, ids, cond, torch.tensor(0.5), 0.7)
+        t1 = time.perf_counter()
+        orc.hifigan_forward(hsd, syn.HIFIGAN_COVOMIX, mel)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        one()
+    steps = max(1, min(args.steps, 3))
+    tv, th = 0.0, 0.0
+    for _ in range(steps):
+        a, b = one()
+        tv += a
+        th += b
+    tv /= steps
+    th /= steps
+    sec_per_step = wl["B"] * (n_eval * tv + th)
+    audio_s = wl["B"] * gen_frames / FRAME_RATE
+    value = audio_s / sec_per_step
+    sample = (f"1 of {wl['B']} items, 1 of {n_eval} CFG velocity evaluations ({tv:.2f} s) + vocoder on 1 item ({th:.2f} s), "
+              f"{steps} reps; step time extrapolated = B*(n_eval*t_eval + t_voc)")
+    line = {
+        "impl": "reference", "metric": "audio-seconds/sec (RTF)", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "global_batch": wl["B"], "seq_len": wl["N"]},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ode_step_ms": tv * 1e3 * wl["B"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================== B200 arm
+def run_b200(args):
+    import covomix_b200  # noqa: F401
+    from covomix_b200 import _native as nat, synthetic as syn
+    from covomix_b200.flow import B200FlowSampler
+    from covomix_b200.vocoder import B200Generator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = WORKLOADS[args.workload]
+    cfg, ids_h, cond_h, y0_h, mask_h = make_inputs(wl, seed=30 + rank)     # each rank = its own shard of utterances
+    # weights: identical on every rank (seeded); rank 0 could equally broadcast them (NCCL) -- see DESIGN.md
+    sampler = B200FlowSampler(syn.synthetic_flow_state_dict(cfg, 1234), cfg, dev, torchdiffeq_ode_method=wl["method"],
+                              ode_step_size=1.0 / wl["n_steps"])
+    gen = B200Generator(syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234), syn.HIFIGAN_COVOMIX, dev)
+    B, N, prompt = wl["B"], wl["N"], wl["prompt"]
+    gen_frames = N - prompt
+    audio_s_per_step = B * gen_frames / FRAME_RATE
+
+    ids_d, cond_d, y0_d = ids_h.to(dev), cond_h.to(dev), y0_h.to(dev)
+    ids_p, cond_p = ids_h.pin_memory(), cond_h.pin_memory()
+
+    def step_device():
+        mel = sampler.sample(phoneme_ids=ids_d, cond=cond_d, cond_scale=0.7, y0=y0_d)
+        voc_in = mel[:, prompt:, :].permute(0, 2, 1)           # what the scripts do: sampled[:, mask].permute(0,2,1)
+        return gen(voc_in)
+
+    wav_host = torch.empty(B, 1, gen.out_len(gen_frames), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        i = ids_p.to(dev, non_blocking=True)
+        c = cond_p.to(dev, non_blocking=True)
+        mel = sampler.sample(phoneme_ids=i, cond=c, cond_scale=0.7)   # y0 = torch.randn_like on device, as the reference
+        wav = gen(mel[:, prompt:, :].permute(0, 2, 1))
+        wav_host.copy_(wav, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return wav_host
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler_clock=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler_clock:
+            sampler_clock.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler_clock.stop() if sampler_clock else None
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    W, K = max(args.warmup, 3), args.steps
+    ms_total, clocks = timed(step_device, K, W, ClockSampler(local))
+    ms_step = ms_total / K
+    value = audio_s_per_step * world / (ms_step / 1e3)
+
+    ms_e2e_total, _ = timed(step_e2e, K, 1)
+    ms_e2e = ms_e2e_total / K
+    e2e_value = audio_s_per_step * world / (ms_e2e / 1e3)
+    h2d = ids_p.numel() * 8 + cond_p.numel() * 4
+    d2h = wav_host.numel() * 4
+
+    line = None
+    if rank == 0:
+        # ---- ODE-step latency (one CFG velocity evaluation = 2 network passes batched as 2B), CUDA events
+        x = y0_d
+        for _ in range(2):
+            sampler.velocity(x, times=0.5, phoneme_ids=ids_d, cond=cond_d, cond_scale=0.7)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            sampler.velocity(x, times=0.5, phoneme_ids=ids_d, cond=cond_d, cond_scale=0.7)
+        e1.record()
+        torch.cuda.synchronize()
+        ode_step_ms = e0.elapsed_time(e1) / 3
+
+        # ---- roofline of the dominant kernel: one extra instrumented step (graphs bypassed, every launch of the
+        # step bracketed by CUDA events on the launching stream), same workload, same process
+        with nat.profile() as prof:
+            step_device()
+        pr = prof.result
+        total_kernel_ms = sum(v[0] for v in pr.values())
+        g_ms, g_flops, g_n = pr["gemm_tc"]
+        pk = peaks()
+        achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        flow_fl, voc_fl = algorithmic_flops(cfg, wl)
+        roofline = {
+            "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM: all Linear layers + vocoder convs)",
+            "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tflops"], "peak_source": pk["src"], "traffic": None,
+            "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "algorithmic_flops_per_launch": g_flops / max(g_n, 1),
+            "share_of_step_kernel_time": g_ms / total_kernel_ms if total_kernel_ms else None,
+            "how": "one extra instrumented step after the timed region: CUDA events around every launch on the launching stream",
+            "classes_ms": {k: round(v[0], 3) for k, v in pr.items()},
+            "attention": {"achieved_tflops": pr["attention_tc"][1] / (pr["attention_tc"][0] * 1e-3) / 1e12 if pr["attention_tc"][0] else None,
+                          "launches": pr["attention_tc"][2]},
+            "whole_step": {"algorithmic_tflop": (flow_fl + voc_fl) / 1e12,
+                           "achieved_tflops": (flow_fl + voc_fl) / (ms_step * 1e-3) / 1e12,
+                           "frac_of_peak": (flow_fl + voc_fl) / (ms_step * 1e-3) / 1e12 / pk["tflops"]},
+        }
+        launches = (sampler.launches_per_sample(0.7) + gen.launches_per_forward()) * K
+
+        # ---- CPU baseline on this box's host cores (oracle port, bounded sample)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(wl, cfg)
+
+        line = {
+            "metric": "audio-seconds/sec (RTF)", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 operands / f32 accumulate (flow), fp16 operands / f32 accumulate (vocoder)", "data": "synthetic",
+            "config": {"workload": wl["name"], "global_batch": B * world, "seq_len": N, "parallelism": f"utterance-sharded x{world}",
+                       "cond_scale": 0.7, "l2": "working set (0.8 GB weights + 1.2 GB activations) larger than L2; no flush needed"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "ode_step_ms": ode_step_ms, "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def cpu_baseline(wl, cfg):
+    from covomix_b200 import synthetic as syn
+    from oracle import covomix_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = syn.synthetic_flow_state_dict(cfg, 1234)
+    hsd = syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234)
+    _, ids, cond, y0, _ = make_inputs(dict(wl, B=1))
+    gen_frames = wl["N"] - wl["prompt"]
+    mel = syn.synthetic_logmel(torch.Generator().manual_seed(31), 1, 80, gen_frames)
+    n_eval = wl["n_steps"] * (2 if wl["method"] == "midpoint" else 1)
+    with torch.inference_mode():
+        orc.velocity_cfg(sd, cfg, y0, ids, cond, torch.tensor(0.5), 0.7)      # warm-up
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            orc.velocity_cfg(sd, cfg, y0, ids, cond, torch.tensor(0.5), 0.7)
+        tv = (time.perf_counter() - t0) / reps
+    orc.hifigan_forward(hsd, syn.HIFIGAN_COVOMIX, mel)
+    t0 = time.perf_counter()
+    orc.hifigan_forward(hsd, syn.HIFIGAN_COVOMIX, mel)
+    th = time.perf_counter() - t0
+    sec = wl["B"] * (n_eval * tv + th)
+    return {"value": wl["B"] * gen_frames / FRAME_RATE / sec, "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": f"1 of {wl['B']} items, 1 of {n_eval} CFG velocity evaluations ({tv:.2f} s, fp32 torch CPU) + vocoder on 1 item "
+                      f"({th:.2f} s); extrapolated linearly to the full step",
+            "ode_step_ms_b1": tv * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

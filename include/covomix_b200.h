@@ -121,6 +121,14 @@ int covo_hifigan_launches_per_forward(const covo_hifigan* h);
 const char* covo_last_error(void);
 int covo_version(void);
 
+/* ---- launch profiler (bench.py's roofline leg) -----------------------------------------------------------
+ * Between covo_prof_begin() and covo_prof_end() every kernel launch is bracketed by CUDA events on its stream
+ * (CUDA graphs are bypassed).  Classes: 0 tcgen05 GEMM, 1 attention, 2 RMSNorm/AdaLN, 3 conv-pos, 4 element-wise,
+ * 5 per-call prologue.  covo_prof_end synchronises the device and returns, per class, the summed kernel time (ms),
+ * the summed algorithmic FLOPs and the launch count. */
+int covo_prof_begin(void);
+int covo_prof_end(double* ms_per_class, double* flops_per_class, int* launches_per_class, int n_classes);
+
 /* ---- kernel-level test hooks (used only by tests/ to check single kernels against torch) -------------
  * D[M,N] = A[M,K] * W[N,K]^T (+bias) (+residual), bf16 operands, fp32 accumulate, via the tcgen05 kernel. */
 int covo_dbg_gemm(const void* A_bf16, const void* W_bf16, const float* bias, const float* residual, float* out_f32,

@@ -20,7 +20,7 @@ EXPORTS = (
     "covo_flow_create", "covo_flow_destroy", "covo_flow_workspace_bytes", "covo_flow_sample", "covo_flow_velocity",
     "covo_flow_launches_per_sample", "covo_hifigan_create", "covo_hifigan_destroy", "covo_hifigan_workspace_bytes",
     "covo_hifigan_out_len", "covo_hifigan_forward", "covo_hifigan_launches_per_forward", "covo_last_error",
-    "covo_version", "covo_dbg_gemm", "covo_dbg_attention",
+    "covo_version", "covo_dbg_gemm", "covo_dbg_attention", "covo_prof_begin", "covo_prof_end",
 )
 
 
@@ -71,12 +71,33 @@ def lib() -> C.CDLL:
     L.covo_hifigan_launches_per_forward.argtypes = [vp]
     L.covo_dbg_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.covo_dbg_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.covo_prof_begin.argtypes = []
+    L.covo_prof_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), i32]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("covo_version",):
             fn.restype = i32
     _lib = L
     return L
+
+
+PROF_CLASSES = ("gemm_tc", "attention_tc", "rmsnorm", "convpos", "elementwise", "prologue")
+
+
+class profile:
+    """Context manager around covo_prof_begin/_end; ``.result`` maps class -> (ms, flops, launches)."""
+
+    def __enter__(self):
+        check(lib().covo_prof_begin(), "covo_prof_begin")
+        self.result = {}
+        return self
+
+    def __exit__(self, *exc):
+        n = len(PROF_CLASSES)
+        ms, fl, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int * n)()
+        check(lib().covo_prof_end(ms, fl, cnt, n), "covo_prof_end")
+        self.result = {PROF_CLASSES[i]: (ms[i], fl[i], cnt[i]) for i in range(n)}
+        return False
 
 
 def check(rc: int, what: str):

@@ -147,6 +147,43 @@ inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
     return COVO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ launch profiler
+// Opt-in (covo_prof_begin/_end): brackets every kernel launch with CUDA events on the launching stream so that
+// bench.py can report per-kernel-class time shares and the dominant kernel's achieved FLOP/s.  Off in normal use.
+enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_NORM = 2, PC_CONVPOS = 3, PC_ELEMWISE = 4, PC_PROLOGUE = 5, PC_COUNT = 6 };
+struct ProfRec {
+    int cat;
+    double flops;
+    cudaEvent_t e0, e1;
+};
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+};
+inline Profiler& prof() {
+    static Profiler p;
+    return p;
+}
+struct ProfScope {
+    cudaStream_t st;
+    int idx = -1;
+    ProfScope(int cat, double flops, cudaStream_t s) : st(s) {
+        Profiler& p = prof();
+        if (!p.on) return;
+        ProfRec r;
+        r.cat = cat;
+        r.flops = flops;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        p.recs.push_back(r);
+        idx = static_cast<int>(p.recs.size()) - 1;
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(prof().recs[idx].e1, st);
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ GEMM ops
 struct DeviceInfo {
     int device = 0;
@@ -167,6 +204,7 @@ struct GemmOp {
     int bn = 256;
     int fmt = 1;             // 0 fp16, 1 bf16
     int grid = 1;
+    double flops = 0.0;      // algorithmic FLOPs of this launch (real channels only; padding does not count)
 };
 
 template <int BN, int FMT>
@@ -237,6 +275,7 @@ inline void gemm_defaults(GemmArgs& g) {
 }
 
 inline int launch_gemm(const GemmOp& op, cudaStream_t st) {
+    ProfScope ps(PC_GEMM, op.flops, st);
 #define COVO_LAUNCH(BN_, F_)                                                                              \
     do {                                                                                                  \
         COVO_TRY((set_gemm_attr<BN_, F_>()));                                                             \

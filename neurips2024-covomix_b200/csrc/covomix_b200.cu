@@ -115,7 +115,7 @@ int covo_flow_sample(covo_flow* h, const int64_t* ids, const float* cond, const 
     COVO_CK(cudaMemcpyAsync(p->ids, ids, bn * c.n_streams * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     COVO_CK(cudaMemcpyAsync(p->cond, cond, bn * c.dim_in * sizeof(float), cudaMemcpyDeviceToDevice, st));
     COVO_CK(cudaMemcpyAsync(p->x_state, y0, bn * c.dim_x * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (p->exec) {
+    if (p->exec && !prof().on) {
         COVO_CK(cudaGraphLaunch(p->exec, st));
     } else {
         int launches = 0;
@@ -214,6 +214,38 @@ int covo_hifigan_forward(covo_hifigan* h, const float* mel, void* wav, int B, in
     HifiPlan* p = nullptr;
     COVO_TRY(hifi_get_plan(h, B, T, workspace, workspace_bytes, &p));
     return hifi_enqueue(h, *p, mel, wav, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+// ====================================================================================== profiler
+int covo_prof_begin(void) {
+    Profiler& p = prof();
+    p.recs.clear();
+    p.on = true;
+    return COVO_OK;
+}
+
+int covo_prof_end(double* ms_per_class, double* flops_per_class, int* launches_per_class, int n_classes) {
+    Profiler& p = prof();
+    p.on = false;
+    COVO_CK(cudaDeviceSynchronize());
+    for (int i = 0; i < n_classes; ++i) {
+        ms_per_class[i] = 0.0;
+        flops_per_class[i] = 0.0;
+        launches_per_class[i] = 0;
+    }
+    for (ProfRec& r : p.recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (r.cat < n_classes) {
+            ms_per_class[r.cat] += ms;
+            flops_per_class[r.cat] += r.flops;
+            launches_per_class[r.cat] += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    p.recs.clear();
+    return COVO_OK;
 }
 
 // ====================================================================================== test hooks

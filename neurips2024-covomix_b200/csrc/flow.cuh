@@ -186,12 +186,14 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
     plain_out(p.op_const.args, M, D, D);
     p.op_const.args.bias = h->embed_b.as<float>();
     p.op_const.args.out_f32 = p.e_const;
+    p.op_const.flops = 2.0 * M * D * (c.n_streams * c.dim_phoneme_emb + c.dim_in);
     // per-evaluation part: h0 = x W_x^T + e_const
     gemm_defaults(p.op_embed.args);
     COVO_TRY(build_gemm(p.op_embed, h->di, a2d(p.xin, h->ldx, M), M, 1, h->embed_wx.ptr, D, 1, 0));
     plain_out(p.op_embed.args, M, D, D);
     p.op_embed.args.residual = p.e_const;
     p.op_embed.args.out_f32 = p.h0;
+    p.op_embed.flops = 2.0 * M * D * c.dim_x;
 
     p.op_skip.assign(c.depth, GemmOp());
     p.op_qkv.assign(c.depth, GemmOp());
@@ -218,6 +220,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             plain_out(op.args, M, D, D);
             op.args.bias = lw.skip_b.as<float>();
             op.args.out_f32 = p.x;
+            op.flops = 2.0 * M * D * 2 * D;
         }
         {
             GemmOp& op = p.op_qkv[L];
@@ -228,6 +231,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             op.args.rope = p.rope;
             op.args.rope_seq = p.N;
             op.args.rope_cols = 2 * inner;
+            op.flops = 2.0 * M * 3 * inner * D;
         }
         {
             GemmOp& op = p.op_out[L];
@@ -236,6 +240,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             plain_out(op.args, M, D, D);
             op.args.residual = p.x;
             op.args.out_f32 = p.x;
+            op.flops = 2.0 * M * D * inner;
         }
         {
             GemmOp& op = p.op_ff1[L];
@@ -245,6 +250,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             op.args.bias = lw.ff1_b.as<float>();
             op.args.out_h = p.ffh;
             op.args.act_h = ACT_GELU;
+            op.flops = 2.0 * M * D * c.ff_mult * D;
         }
         {
             GemmOp& op = p.op_ff2[L];
@@ -254,6 +260,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             op.args.bias = lw.ff2_b.as<float>();
             op.args.residual = p.x;
             op.args.out_f32 = p.x;
+            op.flops = 2.0 * M * D * c.ff_mult * D;
             // bf16 copy of the next layer's input: a skip slot (first half) or the "current" slot (second half)
             if (L + 1 < c.depth) {
                 const int slot = (L + 1 < half) ? (L + 1) : half;
@@ -265,6 +272,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
     COVO_TRY(build_gemm(p.op_pred, h->di, a2d(p.a_norm, D, M), M, 1, h->pred_w.ptr, h->npred, 1, 0));
     plain_out(p.op_pred.args, M, c.dim_x, c.dim_x);
     p.op_pred.args.out_f32 = p.vpred;
+    p.op_pred.flops = 2.0 * M * D * c.dim_x;
 
     // attention
     {
@@ -283,6 +291,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
 
 inline int launch_attention(const covo_flow* h, const FlowPlan& p, cudaStream_t st) {
     const int Bt = p.M / p.N;
+    ProfScope ps(PC_ATTN, 4.0 * p.N * static_cast<double>(p.N) * h->cfg.dim_head * h->cfg.heads * Bt, st);
     if (h->naive_attn) {
         dim3 grid(ceil_div(p.N, 8), h->cfg.heads, Bt);
         naive_attention_kernel<<<grid, 256, 0, st>>>(p.qkv, p.attn_o, p.N, h->cfg.heads, p.attn.inner,
@@ -305,6 +314,7 @@ inline void launch_rmsnorm_v(const float* x, const float* g, const float* b, __n
     rmsnorm_kernel<V><<<ceil_div(M, 8), 256, 0, st>>>(x, g, b, out, M);
 }
 inline int launch_rmsnorm(const float* x, const float* g, const float* b, __nv_bfloat16* out, int M, int D, cudaStream_t st) {
+    ProfScope ps(PC_NORM, 0.0, st);
     switch (D / 128) {
         case 8: launch_rmsnorm_v<8>(x, g, b, out, M, st); break;
         case 4: launch_rmsnorm_v<4>(x, g, b, out, M, st); break;
@@ -321,6 +331,7 @@ inline int flow_enqueue_prologue(covo_flow* h, FlowPlan& p, cudaStream_t st, int
     const covo_flow_cfg& c = h->cfg;
     const int D = c.dim;
     TimesArg ta;
+    ProfScope* ps = new ProfScope(PC_PROLOGUE, 0.0, st);
     memcpy(ta.t, p.times, sizeof(float) * p.n_t);
     set_times_kernel<<<1, FLOW_MAX_TIMES, 0, st>>>(p.d_times, ta, p.n_t);
     time_features_kernel<<<p.n_t, 256, 0, st>>>(p.d_times, h->time_w.as<float>(), p.tfeat, p.n_t, D / 2);
@@ -337,6 +348,7 @@ inline int flow_enqueue_prologue(covo_flow* h, FlowPlan& p, cudaStream_t st, int
     rope_table_kernel<<<ceil_div(p.N * 32, 256), 256, 0, st>>>(h->inv_freq.as<float>(), p.rope, p.N, 32);
     embed_input_kernel<<<p.M, 256, 0, st>>>(p.ids, p.cond, h->emb_table.as<float>(), h->null_cond.as<float>(), p.a_pc, p.BN,
                                             c.n_streams, c.dim_phoneme_emb, c.dim_in, c.num_phoneme_tokens, h->kpc);
+    delete ps;
     COVO_CK(cudaGetLastError());
     COVO_TRY(launch_gemm(p.op_const, st));
     *launches += 7;
@@ -350,6 +362,7 @@ inline int flow_enqueue_network(covo_flow* h, FlowPlan& p, int t_idx, cudaStream
     const int Bt = M / p.N;
     COVO_TRY(launch_gemm(p.op_embed, st));
     {
+        ProfScope ps(PC_CONVPOS, 0.0, st);
         dim3 g(ceil_div(D, 256), ceil_div(p.N, 8), Bt);
         convpos_kernel<31, 8><<<g, 256, 0, st>>>(p.h0, h->conv_wT.as<float>(), h->conv_b.as<float>(), p.x, p.slots, p.N, D);
         COVO_CK(cudaGetLastError());
@@ -382,7 +395,10 @@ inline int flow_enqueue_sample(covo_flow* h, FlowPlan& p, cudaStream_t st, int* 
     const int n_el = p.BN * c.dim_x;
     const int eb = ceil_div(n_el, 256);
     COVO_TRY(flow_enqueue_prologue(h, p, st, launches));
-    state_to_input_kernel<<<eb, 256, 0, st>>>(p.x_state, p.xin, p.BN, c.dim_x, h->ldx, p.two_branch);
+    {
+        ProfScope ps(PC_ELEMWISE, 0.0, st);
+        state_to_input_kernel<<<eb, 256, 0, st>>>(p.x_state, p.xin, p.BN, c.dim_x, h->ldx, p.two_branch);
+    }
     ++*launches;
     int ti = 0;
     for (int k = 0; k < p.n_steps; ++k) {
@@ -390,20 +406,29 @@ inline int flow_enqueue_sample(covo_flow* h, FlowPlan& p, cudaStream_t st, int* 
             const float dt = p.dts[ti];
             COVO_TRY(flow_enqueue_network(h, p, ti, st, launches));
             // y_mid = y0 + f0 * dt/2 -> network input only
-            cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, nullptr, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
+            {
+                ProfScope ps(PC_ELEMWISE, 0.0, st);
+                cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, nullptr, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
                                                   p.cond_scale, 0.5f * dt, p.two_branch);
+            }
             ++ti;
             COVO_TRY(flow_enqueue_network(h, p, ti, st, launches));
             // y1 = y0 + dt * f(t0 + dt/2, y_mid)
-            cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, p.x_state, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
+            {
+                ProfScope ps(PC_ELEMWISE, 0.0, st);
+                cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, p.x_state, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
                                                   p.cond_scale, dt, p.two_branch);
+            }
             ++ti;
             *launches += 2;
         } else {
             const float dt = p.dts[ti];
             COVO_TRY(flow_enqueue_network(h, p, ti, st, launches));
-            cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, p.x_state, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
+            {
+                ProfScope ps(PC_ELEMWISE, 0.0, st);
+                cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, p.x_state, p.x_state, nullptr, p.xin, p.BN, c.dim_x, h->ldx,
                                                   p.cond_scale, dt, p.two_branch);
+            }
             ++ti;
             ++*launches;
         }
@@ -417,10 +442,16 @@ inline int flow_enqueue_velocity(covo_flow* h, FlowPlan& p, cudaStream_t st, int
     const int n_el = p.BN * c.dim_x;
     const int eb = ceil_div(n_el, 256);
     COVO_TRY(flow_enqueue_prologue(h, p, st, launches));
-    state_to_input_kernel<<<eb, 256, 0, st>>>(p.x_in, p.xin, p.BN, c.dim_x, h->ldx, p.two_branch);
+    {
+        ProfScope ps(PC_ELEMWISE, 0.0, st);
+        state_to_input_kernel<<<eb, 256, 0, st>>>(p.x_in, p.xin, p.BN, c.dim_x, h->ldx, p.two_branch);
+    }
     COVO_TRY(flow_enqueue_network(h, p, 0, st, launches));
-    cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, nullptr, nullptr, p.v_out, nullptr, p.BN, c.dim_x, h->ldx, p.cond_scale,
+    {
+        ProfScope ps(PC_ELEMWISE, 0.0, st);
+        cfg_update_kernel<<<eb, 256, 0, st>>>(p.vpred, nullptr, nullptr, p.v_out, nullptr, p.BN, c.dim_x, h->ldx, p.cond_scale,
                                           0.f, p.two_branch);
+    }
     COVO_CK(cudaGetLastError());
     *launches += 2;
     return COVO_OK;

@@ -120,6 +120,7 @@ inline int hifi_conv_op(const covo_hifigan* h, GemmOp& op, const void* act, int 
     op.args.h_is_fp16 = h->is_fp16;
     return COVO_OK;
 }
+inline double conv_flops(int B, int T, int cin, int cout, int k) { return 2.0 * B * T * static_cast<double>(cin) * cout * k; }
 
 inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
     const covo_hifigan_cfg& c = h->cfg;
@@ -133,6 +134,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
     p.pre.args.out_h = p.pre_act;                               // x = lrelu(conv_pre(mel)) (models.py:101-103)
     p.pre.args.act_h = ACT_LRELU;
     p.pre.args.slope = 0.1f;
+    p.pre.flops = conv_flops(p.B, p.T, c.num_mels, hifi_chan(c, -1), 7);
     p.launches = 2;                                             // mel transpose + conv_pre
 
     for (int i = 0; i < c.num_upsamples; ++i) {
@@ -166,6 +168,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
             op.args.act_h = ACT_LRELU;
             op.args.slope = 0.1f;
             op.args.h_is_fp16 = h->is_fp16;
+            op.flops = conv_flops(p.B, s.t_in, hifi_chan(c, i - 1), s.c_out, s.ksize);
             ++p.launches;
         }
         // ---- resblocks
@@ -187,6 +190,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
                     COVO_TRY(hifi_conv_op(h, o1, in1, s.c_out_pad, s.t_out, p.B, tw, tb, s.c_out_pad, k, d));
                     o1.args.out_h = s.hr[j];
                     o1.args.act_h = ACT_LRELU;
+                    o1.flops = conv_flops(p.B, s.t_out, s.c_out, s.c_out, k);
                     s.convs.push_back(o1);
                     COVO_TRY(w.get(n2 + ".w", hdt, &tw));
                     COVO_TRY(w.get(n2 + ".b", DT_F32, &tb));
@@ -198,6 +202,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
                         o2.args.out_h = s.ar[j];
                         o2.args.act_h = ACT_LRELU;
                     }
+                    o2.flops = conv_flops(p.B, s.t_out, s.c_out, s.c_out, k);
                     s.convs.push_back(o2);
                 } else {
                     // xt = c(lrelu(x)); x = xt + x                   (models.py:63-68)
@@ -212,6 +217,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
                         o1.args.out_h = s.ar[j];
                         o1.args.act_h = ACT_LRELU;
                     }
+                    o1.flops = conv_flops(p.B, s.t_out, s.c_out, s.c_out, k);
                     s.convs.push_back(o1);
                 }
             }
@@ -257,6 +263,7 @@ inline int hifi_get_plan(covo_hifigan* h, int B, int T, void* ws, size_t ws_byte
 inline int hifi_enqueue(covo_hifigan* h, HifiPlan& p, const float* mel, void* wav, int out_dtype, cudaStream_t st) {
     const covo_hifigan_cfg& c = h->cfg;
     {
+        ProfScope ps(PC_ELEMWISE, 0.0, st);
         dim3 g(ceil_div(p.T, 32), ceil_div(c.num_mels, 32), p.B);
         mel_to_tc_kernel<<<g, 256, 0, st>>>(mel, p.mel_tc, c.num_mels, p.T, h->mel_pad, h->is_fp16);
         COVO_CK(cudaGetLastError());
@@ -268,6 +275,7 @@ inline int hifi_enqueue(covo_hifigan* h, HifiPlan& p, const float* mel, void* wa
         for (const GemmOp& op : s.convs) COVO_TRY(launch_gemm(op, st));
         const size_t n4 = static_cast<size_t>(p.B) * s.t_out * s.c_out_pad / 4;
         const float slope = (i + 1 == c.num_upsamples) ? 0.01f : 0.1f;     // models.py:103 vs :112 (F.leaky_relu default)
+        ProfScope ps(PC_ELEMWISE, 0.0, st);
         stage_mean_act_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
             s.xr[0], c.num_kernels > 1 ? s.xr[1] : nullptr, c.num_kernels > 2 ? s.xr[2] : nullptr, s.out_act, n4,
             1.0f / static_cast<float>(c.num_kernels), slope, h->is_fp16);
@@ -278,6 +286,7 @@ inline int hifi_enqueue(covo_hifigan* h, HifiPlan& p, const float* mel, void* wa
         Tensor tw, tb;
         COVO_TRY(h->w.get("conv_post.w", DT_F32, &tw));
         COVO_TRY(h->w.get("conv_post.b", DT_F32, &tb));
+        ProfScope ps(PC_ELEMWISE, conv_flops(p.B, s.t_out, s.c_out, 1, 7), st);
         dim3 g(ceil_div(s.t_out, 256), p.B);
         conv_post_kernel<<<g, 256, 7 * s.c_out_pad * sizeof(float), st>>>(s.out_act, tw.as<float>(), tb.as<float>(), wav, s.t_out,
                                                                           s.c_out_pad, s.c_out_pad, h->is_fp16, out_dtype);

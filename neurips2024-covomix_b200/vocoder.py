@@ -22,7 +22,7 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 
 class B200Generator:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: HifiganConfig = HIFIGAN_COVOMIX, device="cuda:0",
-                 h_format: str = "bf16"):
+                 h_format: str = "fp16"):
         self.h = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":

@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors produced by the
+real reference modules and against the CPU oracle on the same seeded inputs.
+
+Tolerances (reference arithmetic is fp32; ours is bf16/fp16 operands with fp32 accumulation):
+  one velocity evaluation   rel-L2 <= 1e-2, max-abs <= 5e-2 * std(v)
+  sampled mel (32 NFE)      rel-L2 <= 3e-2, mean-abs <= 0.05
+  waveform                  rel-L2 <= 2e-3 (fp16 operands, default) / 1e-2 (bf16 operands)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import covomix_b200  # noqa: F401
+from covomix_b200 import _native as nat, synthetic as syn
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+P = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import covomix_oracle
+    return covomix_oracle
+
+
+@pytest.fixture(scope="module")
+def vosingle(dev):
+    from covomix_b200.flow import B200FlowSampler
+    sd = syn.synthetic_flow_state_dict(syn.VOSINGLE, 1234)
+    return sd, B200FlowSampler(sd, syn.VOSINGLE, dev)
+
+
+@pytest.fixture(scope="module")
+def vomix(dev):
+    from covomix_b200.flow import B200FlowSampler
+    sd = syn.synthetic_flow_state_dict(syn.VOMIX, 1234)
+    return sd, B200FlowSampler(sd, syn.VOMIX, dev)
+
+
+@pytest.fixture(scope="module")
+def vocoder(dev):
+    from covomix_b200.vocoder import B200Generator
+    sd = syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234)
+    return sd, B200Generator(sd, syn.HIFIGAN_COVOMIX, dev)
+
+
+# ------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (1, 64, 64, 0), (129, 256, 128, 128), (300, 512, 1024, 0),
+                                      (2600, 3072, 1024, 256), (1300, 1024, 4096, 0)])
+def test_gemm_kernel(dev, M, N, K, bn):
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
+    bias, res = torch.randn(N, device=dev), torch.randn(M, N, device=dev)
+    out = torch.full((M, N), float("nan"), device=dev)
+    outh = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    nat.check(nat.lib().covo_dbg_gemm(P(A), P(W), P(bias), P(res), P(out), P(outh), M, N, K, 1, bn, None), "gemm")
+    ref = A.float() @ W.float().t() + bias + res
+    assert rel_l2(out, ref) < 1e-5                      # same bf16 inputs, fp32 accumulate: only summation order differs
+    assert rel_l2(outh.float(), torch.nn.functional.gelu(ref)) < 4e-3
+
+
+@pytest.mark.parametrize("Bt,N,H", [(1, 1, 1), (1, 127, 2), (2, 128, 1), (1, 129, 1), (3, 650, 16), (2, 1650, 16)])
+def test_attention_kernel(dev, Bt, N, H):
+    torch.manual_seed(N)
+    qkv = torch.randn(Bt, N, 3 * H * 64, device=dev).bfloat16()
+    out = torch.zeros(Bt, N, H * 64, device=dev, dtype=torch.bfloat16)
+    nat.check(nat.lib().covo_dbg_attention(P(qkv), P(out), Bt, N, H, 0, None), "attention")
+    q, k, v = (t.reshape(Bt, N, H, 64).permute(0, 2, 1, 3).float() for t in qkv.chunk(3, dim=-1))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).permute(0, 2, 1, 3).reshape(Bt, N, H * 64)
+    assert rel_l2(out.float(), ref) < 5e-3              # P and O rounded to bf16
+
+
+# ------------------------------------------------------------------------------------------ flow vs reference golden
+@pytest.mark.parametrize("name", ["vosingle", "vomix"])
+def test_velocity_matches_reference(dev, name, vosingle, vomix):
+    sd, smp = vosingle if name == "vosingle" else vomix
+    g = np.load(os.path.join(GOLDEN, f"flow_{name}.npz"))
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(smp.cfg, int(g["B"]), int(g["N"]), prompt=int(g["prompt"]),
+                                                 seed=int(g["input_seed"]))
+    v = smp.velocity(y0.to(dev), times=float(g["t"]), phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+    ref = torch.from_numpy(g["v_cfg"])
+    assert rel_l2(v, ref) < 1e-2
+    assert float((v.cpu() - ref).abs().max()) < 5e-2 * float(ref.std())
+    v1 = smp.velocity(y0.to(dev), times=float(g["t"]), phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=1.0)
+    assert rel_l2(v1, g["v_cond"]) < 1e-2               # cond_scale == 1 -> conditional branch only (acoustic.py:423)
+
+
+@pytest.mark.parametrize("name", ["vosingle", "vomix"])
+def test_sample_matches_reference(dev, name, vosingle, vomix):
+    sd, smp = vosingle if name == "vosingle" else vomix
+    g = np.load(os.path.join(GOLDEN, f"flow_{name}.npz"))
+    ids, cond, _, mask = syn.synthetic_flow_inputs(smp.cfg, int(g["B"]), int(g["N"]), prompt=int(g["prompt"]),
+                                                   seed=int(g["input_seed"]))
+    mel = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), mask=mask.to(dev), cond_scale=0.7,
+                     y0=torch.from_numpy(g["y0_sample"]).to(dev))       # reference default: midpoint, h = 1/16, 32 NFE
+    ref = torch.from_numpy(g["mel"])
+    assert mel.shape == ref.shape
+    assert rel_l2(mel, ref) < 3e-2
+    assert float((mel.cpu() - ref).abs().mean()) < 0.05
+    # calling again (CUDA-graph replay) is deterministic
+    mel2 = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), mask=mask.to(dev), cond_scale=0.7,
+                      y0=torch.from_numpy(g["y0_sample"]).to(dev))
+    assert torch.equal(mel, mel2)
+
+
+@pytest.mark.parametrize("N", [1, 31, 130])
+def test_euler_sample_vs_oracle_ragged_lengths(dev, orc, vosingle, N):
+    from covomix_b200.flow import B200FlowSampler
+    sd, _ = vosingle
+    smp = B200FlowSampler(sd, syn.VOSINGLE, dev, torchdiffeq_ode_method="euler", ode_step_size=0.25)
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, 2, N, prompt=min(8, N), seed=N)
+    mel = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+    ref = orc.flow_sample(sd, syn.VOSINGLE, ids, cond, y0, cond_scale=0.7, method="euler", step_size=0.25)
+    assert rel_l2(mel, ref) < 3e-2
+    smp.close()
+
+
+def test_flow_argument_errors(dev, vosingle):
+    _, smp = vosingle
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, 1, 16, prompt=4)
+    with pytest.raises(ValueError):
+        smp.sample(phoneme_ids=ids[:, :8].to(dev), cond=cond.to(dev))
+    with pytest.raises(ValueError):
+        smp.sample(phoneme_ids=ids.to(dev), cond=cond[:, :, :40].to(dev))
+    ws = torch.empty(1024, dtype=torch.uint8, device=dev)
+    out = torch.empty(1, 16, 80, device=dev)
+    rc = nat.lib().covo_flow_sample(smp._h, P(ids.to(dev)), P(cond.to(dev)), P(y0.to(dev)), P(out), 1, 16, 1, 16, 0.7,
+                                    P(ws), ws.numel(), None)
+    assert rc == -1 and b"workspace too small" in nat.lib().covo_last_error()
+
+
+# ------------------------------------------------------------------------------------------ flow, full-size properties
+def test_c3_batch_items_are_independent(dev, vomix):
+    """BASELINE config C3 shape (B=8, N=1650): each item's velocity must equal the B=1 evaluation of that item."""
+    _, smp = vomix
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOMIX, 8, 1650, prompt=150, seed=30)
+    v = smp.velocity(y0.to(dev), times=0.5, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+    assert torch.isfinite(v).all()
+    for b in (0, 7):
+        vb = smp.velocity(y0[b:b + 1].to(dev), times=0.5, phoneme_ids=ids[b:b + 1].to(dev), cond=cond[b:b + 1].to(dev),
+                          cond_scale=0.7)
+        assert rel_l2(v[b:b + 1], vb) < 1e-5
+
+
+def test_cfg_linearity(dev, vosingle):
+    """v(s) = (1+s) v_c - s v_n is affine in s: v(0.7) == v(0) + 0.7/0.3 * (v(0.3) - v(0))."""
+    _, smp = vosingle
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, 1, 200, prompt=50, seed=4)
+    f = lambda s: smp.velocity(y0.to(dev), times=0.25, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=s)
+    v0, v3, v7 = f(0.0), f(0.3), f(0.7)
+    assert rel_l2(v7, v0 + (0.7 / 0.3) * (v3 - v0)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ vocoder
+def test_hifigan_matches_reference(dev, vocoder):
+    sd, gen = vocoder
+    g = np.load(os.path.join(GOLDEN, "hifigan.npz"))
+    rng = torch.Generator().manual_seed(int(g["input_seed"]))
+    mels = [syn.synthetic_logmel(rng, 1, 80, 256), syn.synthetic_logmel(rng, 80, 64), syn.synthetic_logmel(rng, 2, 80, 48)]
+    for mel, key in zip(mels, ("wav_c1", "wav_unbatched", "wav_batch")):
+        wav = gen(mel.to(dev))
+        ref = torch.from_numpy(g[key])
+        assert wav.numel() == ref.numel() and wav.shape[-1] == 160 * mel.shape[-1] + 32
+        assert wav.shape == (mel.shape[0] if mel.ndim == 3 else 1, 1, ref.shape[-1])
+        assert rel_l2(wav.reshape(-1), ref.reshape(-1)) < 2e-3
+        # mel_decode_to_wav semantics (x32768 -> int16): fused i16 output == host-side cast of our own f32 output
+        i16 = gen(mel.to(dev), out_dtype="i16").cpu().numpy().reshape(-1)
+        host = (wav.reshape(-1) * 32768.0).cpu().numpy().astype("int16")
+        assert np.array_equal(i16, host)
+        ri = (ref.reshape(-1) * 32768.0).numpy().astype("int16").astype(np.int64)
+        close = np.abs(i16.astype(np.int64) - ri) <= np.maximum(4, np.abs(ri) / 64)
+        assert close.mean() > 0.99
+        f16 = gen(mel.to(dev), out_dtype="f16")
+        assert torch.equal(f16, wav.half())
+
+
+def test_hifigan_bf16_operands(dev):
+    from covomix_b200.vocoder import B200Generator
+    g = np.load(os.path.join(GOLDEN, "hifigan.npz"))
+    sd = syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234)
+    gen = B200Generator(sd, syn.HIFIGAN_COVOMIX, dev, h_format="bf16")
+    mel = syn.synthetic_logmel(torch.Generator().manual_seed(int(g["input_seed"])), 1, 80, 256)
+    assert rel_l2(gen(mel.to(dev)).reshape(-1), g["wav_c1"].reshape(-1)) < 1e-2
+    gen.close()
+
+
+@pytest.mark.parametrize("T", [1, 2, 7])
+def test_hifigan_tiny_lengths(dev, orc, vocoder, T):
+    sd, gen = vocoder
+    mel = syn.synthetic_logmel(torch.Generator().manual_seed(T), 3, 80, T)
+    assert rel_l2(gen(mel.to(dev)), orc.hifigan_forward(sd, syn.HIFIGAN_COVOMIX, mel)) < 2e-3
+
+
+def test_hifigan_resblock2_config(dev, orc):
+    """config_v3-style generator: ResBlock2 (models.py:51-72), different rates / kernels / channel counts."""
+    from covomix_b200.vocoder import B200Generator
+    cfg = syn.HifiganConfig(resblock="2", upsample_rates=(8, 8, 4), upsample_kernel_sizes=(16, 16, 8),
+                            upsample_initial_channel=256, resblock_kernel_sizes=(3, 5, 7),
+                            resblock_dilation_sizes=((1, 2), (2, 6), (3, 12)))
+    sd = syn.synthetic_hifigan_state_dict(cfg, 5)
+    gen = B200Generator(sd, cfg, dev)
+    mel = syn.synthetic_logmel(torch.Generator().manual_seed(9), 2, 80, 33)
+    wav = gen(mel.to(dev))
+    ref = orc.hifigan_forward(sd, cfg, mel)
+    assert wav.shape == ref.shape == (2, 1, cfg.out_len(33))
+    assert rel_l2(wav, ref) < 2e-3
+    gen.close()
+
+
+def test_hifigan_full_size_properties(dev, vocoder):
+    """C3's vocoder shape [8, 80, 1500] (and C5's T=4096): items are independent, and the generator is local:
+    samples further than the receptive field (~20.4 frames) from a cut are unchanged by the cut."""
+    _, gen = vocoder
+    mel = syn.synthetic_logmel(torch.Generator().manual_seed(11), 8, 80, 1500).to(dev)
+    wav = gen(mel)
+    assert wav.shape == (8, 1, 240032) and torch.isfinite(wav).all() and float(wav.abs().max()) <= 1.0
+    w3 = gen(mel[3:4])
+    assert rel_l2(wav[3:4], w3) < 1e-6
+    crop = gen(mel[3:4, :, :700])
+    keep = (700 - 24) * 160
+    assert rel_l2(crop[..., :keep], w3[..., :keep]) < 1e-6
+    long = gen(syn.synthetic_logmel(torch.Generator().manual_seed(12), 1, 80, 4096).to(dev))
+    assert long.shape == (1, 1, 160 * 4096 + 32) and torch.isfinite(long).all()
