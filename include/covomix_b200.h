@@ -123,8 +123,8 @@ int covo_version(void);
 
 /* ---- launch profiler (bench.py's roofline leg) -----------------------------------------------------------
  * Between covo_prof_begin() and covo_prof_end() every kernel launch is bracketed by CUDA events on its stream
- * (CUDA graphs are bypassed).  Classes: 0 tcgen05 GEMM, 1 attention, 2 RMSNorm/AdaLN, 3 conv-pos, 4 element-wise,
- * 5 per-call prologue.  covo_prof_end synchronises the device and returns, per class, the summed kernel time (ms),
+ * (CUDA graphs are bypassed).  Classes: 0 tcgen05 GEMM (flow), 1 attention, 2 RMSNorm/AdaLN, 3 conv-pos, 4 element-wise,
+ * 5 per-call prologue, 6 tcgen05 GEMM launched by the vocoder.  covo_prof_end synchronises the device and returns, per class, the summed kernel time (ms),
  * the summed algorithmic FLOPs and the launch count. */
 int covo_prof_begin(void);
 int covo_prof_end(double* ms_per_class, double* flops_per_class, int* launches_per_class, int n_classes);

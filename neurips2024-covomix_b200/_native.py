@@ -81,7 +81,7 @@ def lib() -> C.CDLL:
     return L
 
 
-PROF_CLASSES = ("gemm_tc", "attention_tc", "rmsnorm", "convpos", "elementwise", "prologue")
+PROF_CLASSES = ("gemm_tc", "attention_tc", "rmsnorm", "convpos", "elementwise", "prologue", "gemm_tc_vocoder")
 
 
 class profile:

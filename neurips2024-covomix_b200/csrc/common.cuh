@@ -123,9 +123,9 @@ inline EncodeTiledFn encode_fn() {
     }
     return fn;
 }
-// 16-bit tensor, innermost dim contiguous; strides (bytes) for dims 1..rank-1; 128B swizzle.
+// Innermost dim contiguous; strides (bytes) for dims 1..rank-1; 128B swizzle.  dt: 0 = bf16, 1 = fp16, 2 = fp32.
 inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int is_fp16) {
+                     const uint32_t* box, int dt) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(COVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[5], gstr[5];
@@ -140,7 +140,9 @@ inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
         }
     }
     if (reinterpret_cast<uintptr_t>(base) % 16) return fail(COVO_ERR_INVALID, "TMA base not 16-byte aligned");
-    CUresult r = fn(tm, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+    const CUtensorMapDataType cdt = dt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                    : (dt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    CUresult r = fn(tm, cdt, rank,
                     const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(COVO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -150,7 +152,7 @@ inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
 // ------------------------------------------------------------------------------------------------ launch profiler
 // Opt-in (covo_prof_begin/_end): brackets every kernel launch with CUDA events on the launching stream so that
 // bench.py can report per-kernel-class time shares and the dominant kernel's achieved FLOP/s.  Off in normal use.
-enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_NORM = 2, PC_CONVPOS = 3, PC_ELEMWISE = 4, PC_PROLOGUE = 5, PC_COUNT = 6 };
+enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_NORM = 2, PC_CONVPOS = 3, PC_ELEMWISE = 4, PC_PROLOGUE = 5, PC_GEMM_VOC = 6, PC_COUNT = 7 };
 struct ProfRec {
     int cat;
     double flops;
@@ -204,6 +206,7 @@ struct GemmOp {
     int bn = 256;
     int fmt = 1;             // 0 fp16, 1 bf16
     int grid = 1;
+    int cat = PC_GEMM;       // profiler class
     double flops = 0.0;      // algorithmic FLOPs of this launch (real channels only; padding does not count)
 };
 
@@ -274,8 +277,38 @@ inline void gemm_defaults(GemmArgs& g) {
     g.slope = 0.1f;
 }
 
+// Box-shaped outputs [Z][rows][ld] (n contiguous): TMA maps for the fp32 output, the fp32 residual (may be the same
+// buffer) and the 16-bit output.  n_valid columns and `rows` rows are stored; everything else is clipped by TMA.
+inline int gemm_set_outputs(GemmOp& op, float* out_f32, const float* residual, void* out_h, int n_valid, int rows, int Z,
+                            long long ld, long long zs, int h_is_fp16) {
+    GemmArgs& g = op.args;
+    if (residual != nullptr && out_f32 == nullptr) return fail(COVO_ERR_INVALID, "GEMM residual requires an fp32 output");
+    g.n_valid = n_valid;
+    g.scatter = 0;
+    g.has_out_f32 = out_f32 != nullptr;
+    g.has_residual = residual != nullptr;
+    g.has_out_h = out_h != nullptr;
+    g.h_is_fp16 = h_is_fp16;
+    g.out_f32 = out_f32;
+    g.out_h = out_h;
+    if (Z == 1) zs = ld * rows;
+    uint64_t dims[3] = {static_cast<uint64_t>(n_valid), static_cast<uint64_t>(rows), static_cast<uint64_t>(Z)};
+    if (out_f32 != nullptr || residual != nullptr) {
+        uint64_t str[2] = {static_cast<uint64_t>(ld) * 4, static_cast<uint64_t>(zs) * 4};
+        uint32_t box[3] = {32, 32, 1};
+        if (out_f32 != nullptr) COVO_TRY(make_tmap(&g.tmOutF, out_f32, 3, dims, str, box, 2));
+        if (residual != nullptr) COVO_TRY(make_tmap(&g.tmRes, residual, 3, dims, str, box, 2));
+    }
+    if (out_h != nullptr) {
+        uint64_t str[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(zs) * 2};
+        uint32_t box[3] = {64, 32, 1};
+        COVO_TRY(make_tmap(&g.tmOutH, out_h, 3, dims, str, box, h_is_fp16 ? 1 : 0));
+    }
+    return COVO_OK;
+}
+
 inline int launch_gemm(const GemmOp& op, cudaStream_t st) {
-    ProfScope ps(PC_GEMM, op.flops, st);
+    ProfScope ps(op.cat, op.flops, st);
 #define COVO_LAUNCH(BN_, F_)                                                                              \
     do {                                                                                                  \
         COVO_TRY((set_gemm_attr<BN_, F_>()));                                                             \

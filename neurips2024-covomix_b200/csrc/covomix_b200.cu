@@ -249,32 +249,37 @@ int covo_prof_end(double* ms_per_class, double* flops_per_class, int* launches_p
 }
 
 // ====================================================================================== test hooks
+static int dbg_device(DeviceInfo* di) {
+    static bool ready = false;
+    static DeviceInfo cached;
+    if (!ready) {
+        int dev = 0;
+        COVO_CK(cudaGetDevice(&dev));
+        COVO_TRY(check_device(dev, &cached));
+        COVO_TRY(init_kernel_attrs());
+        ready = true;
+    }
+    *di = cached;
+    return COVO_OK;
+}
+
 int covo_dbg_gemm(const void* A_bf16, const void* W_bf16, const float* bias, const float* residual, float* out_f32,
                   void* out_bf16, int M, int N, int K, int act_h, int force_bn, void* stream) {
-    int dev = 0;
-    COVO_CK(cudaGetDevice(&dev));
     DeviceInfo di;
-    COVO_TRY(check_device(dev, &di));
-    COVO_TRY(init_kernel_attrs());
+    COVO_TRY(dbg_device(&di));
     if (N % 64 || K % 64) return fail(COVO_ERR_INVALID, "dbg_gemm needs N, K multiples of 64");
     GemmOp op;
     gemm_defaults(op.args);
     COVO_TRY(build_gemm(op, di, a2d(A_bf16, K, M), M, 1, W_bf16, N, 1, 0, force_bn));
-    plain_out(op.args, M, N, N);
+    COVO_TRY(gemm_set_outputs(op, out_f32, residual, out_bf16, N, M, 1, N, 0, 0));
     op.args.bias = bias;
-    op.args.residual = residual;
-    op.args.out_f32 = out_f32;
-    op.args.out_h = out_bf16;
     op.args.act_h = act_h;
     return launch_gemm(op, static_cast<cudaStream_t>(stream));
 }
 
 int covo_dbg_attention(const void* qkv_bf16, void* out_bf16, int Bt, int N, int heads, int impl, void* stream) {
-    int dev = 0;
-    COVO_CK(cudaGetDevice(&dev));
     DeviceInfo di;
-    COVO_TRY(check_device(dev, &di));
-    COVO_TRY(init_kernel_attrs());
+    COVO_TRY(dbg_device(&di));
     const int inner = heads * 64;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (impl == 1) {

@@ -169,30 +169,19 @@ inline ASource a2d(const void* ptr, int K, int rows) {
     return a;
 }
 
-inline void plain_out(GemmArgs& g, int rows, int n_valid, long long ld) {
-    g.n_valid = n_valid;
-    g.out_zs = 0;
-    g.out_rs = ld;
-    g.out_off = 0;
-    g.t_out = rows;
-}
-
 inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
     const covo_flow_cfg& c = h->cfg;
     const int D = c.dim, inner = c.heads * c.dim_head, M = p.M, half = c.depth / 2;
     // per-call constant part of to_embed:  e_const = [emb | cond] W_pc^T + b
     gemm_defaults(p.op_const.args);
     COVO_TRY(build_gemm(p.op_const, h->di, a2d(p.a_pc, h->kpc, M), M, 1, h->embed_wpc.ptr, D, 1, 0));
-    plain_out(p.op_const.args, M, D, D);
+    COVO_TRY(gemm_set_outputs(p.op_const, p.e_const, nullptr, nullptr, D, M, 1, D, 0, 0));
     p.op_const.args.bias = h->embed_b.as<float>();
-    p.op_const.args.out_f32 = p.e_const;
     p.op_const.flops = 2.0 * M * D * (c.n_streams * c.dim_phoneme_emb + c.dim_in);
     // per-evaluation part: h0 = x W_x^T + e_const
     gemm_defaults(p.op_embed.args);
     COVO_TRY(build_gemm(p.op_embed, h->di, a2d(p.xin, h->ldx, M), M, 1, h->embed_wx.ptr, D, 1, 0));
-    plain_out(p.op_embed.args, M, D, D);
-    p.op_embed.args.residual = p.e_const;
-    p.op_embed.args.out_f32 = p.h0;
+    COVO_TRY(gemm_set_outputs(p.op_embed, p.h0, p.e_const, nullptr, D, M, 1, D, 0, 0));
     p.op_embed.flops = 2.0 * M * D * c.dim_x;
 
     p.op_skip.assign(c.depth, GemmOp());
@@ -217,17 +206,15 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             op.args.tap_row[0] = op.args.tap_row[1] = 0;
             op.args.tap_z[0] = half;                    // current x
             op.args.tap_z[1] = c.depth - 1 - L;         // LIFO pop (acoustic.py:306-310)
-            plain_out(op.args, M, D, D);
+            COVO_TRY(gemm_set_outputs(op, p.x, nullptr, nullptr, D, M, 1, D, 0, 0));
             op.args.bias = lw.skip_b.as<float>();
-            op.args.out_f32 = p.x;
             op.flops = 2.0 * M * D * 2 * D;
         }
         {
             GemmOp& op = p.op_qkv[L];
             gemm_defaults(op.args);
             COVO_TRY(build_gemm(op, h->di, a2d(p.a_norm, D, M), M, 1, lw.qkv_w.ptr, 3 * inner, 1, 0));
-            plain_out(op.args, M, 3 * inner, 3 * inner);
-            op.args.out_h = p.qkv;
+            COVO_TRY(gemm_set_outputs(op, nullptr, nullptr, p.qkv, 3 * inner, M, 1, 3 * inner, 0, 0));
             op.args.rope = p.rope;
             op.args.rope_seq = p.N;
             op.args.rope_cols = 2 * inner;
@@ -237,18 +224,15 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             GemmOp& op = p.op_out[L];
             gemm_defaults(op.args);
             COVO_TRY(build_gemm(op, h->di, a2d(p.attn_o, inner, M), M, 1, lw.out_w.ptr, D, 1, 0));
-            plain_out(op.args, M, D, D);
-            op.args.residual = p.x;
-            op.args.out_f32 = p.x;
+            COVO_TRY(gemm_set_outputs(op, p.x, p.x, nullptr, D, M, 1, D, 0, 0));
             op.flops = 2.0 * M * D * inner;
         }
         {
             GemmOp& op = p.op_ff1[L];
             gemm_defaults(op.args);
             COVO_TRY(build_gemm(op, h->di, a2d(p.a_norm, D, M), M, 1, lw.ff1_w.ptr, D * c.ff_mult, 1, 0));
-            plain_out(op.args, M, D * c.ff_mult, D * c.ff_mult);
+            COVO_TRY(gemm_set_outputs(op, nullptr, nullptr, p.ffh, D * c.ff_mult, M, 1, D * c.ff_mult, 0, 0));
             op.args.bias = lw.ff1_b.as<float>();
-            op.args.out_h = p.ffh;
             op.args.act_h = ACT_GELU;
             op.flops = 2.0 * M * D * c.ff_mult * D;
         }
@@ -256,22 +240,20 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             GemmOp& op = p.op_ff2[L];
             gemm_defaults(op.args);
             COVO_TRY(build_gemm(op, h->di, a2d(p.ffh, D * c.ff_mult, M), M, 1, lw.ff2_w.ptr, D, 1, 0));
-            plain_out(op.args, M, D, D);
-            op.args.bias = lw.ff2_b.as<float>();
-            op.args.residual = p.x;
-            op.args.out_f32 = p.x;
-            op.flops = 2.0 * M * D * c.ff_mult * D;
             // bf16 copy of the next layer's input: a skip slot (first half) or the "current" slot (second half)
+            __nv_bfloat16* next_h = nullptr;
             if (L + 1 < c.depth) {
                 const int slot = (L + 1 < half) ? (L + 1) : half;
-                op.args.out_h = p.slots + static_cast<size_t>(slot) * M * D;
+                next_h = p.slots + static_cast<size_t>(slot) * M * D;
             }
+            COVO_TRY(gemm_set_outputs(op, p.x, p.x, next_h, D, M, 1, D, 0, 0));
+            op.args.bias = lw.ff2_b.as<float>();
+            op.flops = 2.0 * M * D * c.ff_mult * D;
         }
     }
     gemm_defaults(p.op_pred.args);
     COVO_TRY(build_gemm(p.op_pred, h->di, a2d(p.a_norm, D, M), M, 1, h->pred_w.ptr, h->npred, 1, 0));
-    plain_out(p.op_pred.args, M, c.dim_x, c.dim_x);
-    p.op_pred.args.out_f32 = p.vpred;
+    COVO_TRY(gemm_set_outputs(p.op_pred, p.vpred, nullptr, nullptr, c.dim_x, M, 1, c.dim_x, 0, 0));
     p.op_pred.flops = 2.0 * M * D * c.dim_x;
 
     // attention

@@ -8,9 +8,15 @@
 // tap-major by the host).  Accumulation in fp32 in TMEM via tcgen05.mma (cta_group::1,
 // M=128 x N=BN x K=16 per instruction), operands staged by TMA into 128B-swizzled smem through an
 // mbarrier ring; the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
-// main loop of tile i+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (TMEM -> registers -> [RoPE] -> smem transpose -> bias / residual /
-// activation -> coalesced global stores).
+// main loop of tile i+1.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
+// (two warps per TMEM lane quarter, each owning half of the tile's columns).  Epilogue data path:
+// TMEM -> registers (thread = row) -> [RoPE] -> + bias -> + residual (sub-tile TMA-loaded into smem)
+// -> fp32 sub-tile into 128B-swizzled smem -> TMA store; and/or activation -> bf16/fp16 -> smem -> TMA
+// store.  All global traffic of the epilogue is bulk-asynchronous; TMA clips rows/columns that fall
+// outside the output tensor.  ConvTranspose1d outputs (row q, column n -> sample stride*q + n/C - pad)
+// do not form a box and use a per-element store path instead.
 //
 // The same kernel serves every dense contraction on the hot path: the velocity net's Linear layers
 // (taps = 1), its U-Net skip combiner (taps = 2 over two activation slots), HiFi-GAN's dilated
@@ -23,16 +29,21 @@ namespace covo {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;                 // 64 x 2 B = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_MAX_TAPS = 16;
 constexpr int GEMM_STAGE_A_BYTES = GEMM_BM * GEMM_BK * 2;
-constexpr int GEMM_EPI_STAGING_BYTES = 4 * 32 * 64 * 4;   // 4 warps x (32 rows x 64 cols) fp32
+constexpr int GEMM_EPI_BUF_BYTES = 4096;    // per epilogue warp: [32 rows x 128 B], 128B-swizzled
+constexpr int GEMM_EPI_STAGING_BYTES = GEMM_EPI_WARPS * GEMM_EPI_BUF_BYTES;
 
-enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2, ACT_TANH = 3 };
+enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2 };
 
 struct GemmArgs {
     CUtensorMap tmA;                 // (k, row, z) box (64, 128, 1), SWIZZLE_128B
     CUtensorMap tmB;                 // (k, n)      box (64, BN),     SWIZZLE_128B
+    CUtensorMap tmOutF;              // fp32 output   (n, q, z) box (32, 32, 1), SWIZZLE_128B   (if has_out_f32 && !scatter)
+    CUtensorMap tmRes;               // fp32 residual (n, q, z) box (32, 32, 1), SWIZZLE_128B   (if has_residual)
+    CUtensorMap tmOutH;              // 16-bit output (n, q, z) box (64, 32, 1), SWIZZLE_128B   (if has_out_h && !scatter)
     int rows;                        // GEMM rows (q) per z
     int Z;                           // number of z entries (batch items); 1 for Linear layers
     int n_tiles;                     // N_pad / BN
@@ -41,24 +52,24 @@ struct GemmArgs {
     int kc_per_tap;                  // Ktap / 64
     int tap_row[GEMM_MAX_TAPS];
     int tap_z[GEMM_MAX_TAPS];
-    // ---- output mapping: element offset = z*out_zs + q*out_rs + n (shared by f32 / 16-bit / residual)
-    long long out_zs;
-    long long out_rs;
-    long long out_off;               // added to the element offset (ConvTranspose: -pad*Cout)
-    // row validity: 0 <= up_s*q + n/phase_w - up_p < t_out   (plain GEMM: up_s=1, up_p=0, phase_w=1<<30, t_out=rows)
-    int up_s, up_p, phase_w, t_out;
     // ---- epilogue
     const float* bias;               // [N_pad] or null
-    const float* residual;           // fp32, same mapping as the output, or null (may alias out_f32)
-    float* out_f32;                  // or null
-    void* out_h;                     // 16-bit (bf16 or fp16, see h_is_fp16) output or null
-    int act_f32;                     // ACT_NONE | ACT_TANH
+    int has_residual;                // residual added through tmRes (may alias the fp32 output)
+    int has_out_f32;
+    int has_out_h;
     int act_h;                       // ACT_NONE | ACT_GELU | ACT_LRELU   (applied to the 16-bit output only)
     float slope;                     // LeakyReLU slope
     int h_is_fp16;                   // 16-bit output format: 0 = bf16, 1 = fp16
     const float2* rope;              // [seq][32] (cos, sin) or null
     int rope_seq;                    // position = q % rope_seq
     int rope_cols;                   // columns < rope_cols are rotated (q and k of to_qkv)
+    // ---- scatter path (ConvTranspose1d): element offset = z*out_zs + q*out_rs + n + out_off,
+    //      valid iff 0 <= up_s*q + n/phase_w - up_p < t_out
+    int scatter;
+    long long out_zs, out_rs, out_off;
+    int up_s, up_p, phase_w, t_out;
+    float* out_f32;
+    void* out_h;
 };
 
 template <int BN>
@@ -67,7 +78,7 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_STAGING_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_STAGING_BYTES + 512 /*barriers*/ + 1024 /*align*/;
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b, int is_fp16) {
@@ -85,16 +96,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
-    float* staging = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + GEMM_EPI_STAGING_BYTES);
+    uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_STAGING_BYTES);
     uint64_t* full = bars;                         // [STAGES]
     uint64_t* empty = bars + Cfg::STAGES;          // [STAGES]
     uint64_t* tfull = bars + 2 * Cfg::STAGES;      // [2]
     uint64_t* tempty = bars + 2 * Cfg::STAGES + 2; // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+    uint64_t* rbar = bars + 2 * Cfg::STAGES + 4;   // [GEMM_EPI_WARPS] residual sub-tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4 + GEMM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // BN = 64: one 64-column chunk per lane quarter -> only 4 of the 8 epilogue warps have work
+    constexpr int EPI_WARPS_ACTIVE = (BN >= 128) ? GEMM_EPI_WARPS : 4;
 
     const int m_tiles_per_z = (args.rows + GEMM_BM - 1) / GEMM_BM;
     const int total_tiles = args.Z * m_tiles_per_z * args.n_tiles;
@@ -109,8 +123,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], EPI_WARPS_ACTIVE);
         }
+        for (int w = 0; w < GEMM_EPI_WARPS; ++w) mbar_init(&rbar[w], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -179,25 +194,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
-    } else {
-        // ===================================================== epilogue warps (4)
-        const int lq = warp & 3;                       // TMEM lane quarter this warp may access
-        float* stg = staging + (warp - 2) * (32 * 64);
+    } else if (warp - 2 < EPI_WARPS_ACTIVE) {
+        // ===================================================== epilogue warps
+        // warp e = warp-2: TMEM lane quarter lq = warp % 4 (hardware restriction), column half = e / 4.
+        const int e = warp - 2;
+        const int lq = warp & 3;
+        const int chalf = e >> 2;
+        uint8_t* buf = staging + e * GEMM_EPI_BUF_BYTES;          // [32 rows][128 B]; 16-B chunk c of row r at (c ^ (r&7))*16
+        uint8_t* my_row = buf + lane * 128;
+        const int sw = lane & 7;
+        uint64_t* my_rbar = &rbar[e];
+        uint32_t rph = 0;
         int as = 0;
         uint32_t aph = 0;
-        constexpr int CH = 64;
-        constexpr int NCH = BN / CH;
+        constexpr int COLS_PER_WARP = (BN >= 128) ? BN / 2 : BN;
+        constexpr int NCH = COLS_PER_WARP / 64;
+        const bool use_tma = args.scatter == 0;
+        const bool has_res = args.has_residual != 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_idx = tile % args.n_tiles;
             const int mz = tile / args.n_tiles;
             const int m_idx = mz % m_tiles_per_z;
             const int z = mz / m_tiles_per_z;
             const int q_warp0 = m_idx * GEMM_BM + lq * 32;
-            const int n0 = n_idx * BN;
+            const int n0 = n_idx * BN + chalf * COLS_PER_WARP;
+            const bool rows_live = q_warp0 < args.rows;            // warp-uniform: does this warp own any valid row?
+
+            // residual sub-tile of the first fp32 sub-pass: fetched while the MMAs of this tile still run
+            if (has_res && rows_live && n0 < args.n_valid && lane == 0) {
+                bulk_wait_read0();
+                mbar_expect_tx(my_rbar, GEMM_EPI_BUF_BYTES);
+                tma_load_3d(buf, &args.tmRes, my_rbar, n0, q_warp0, z);
+            }
 
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(lq * 32) << 16);
+            const uint32_t t_acc = tmem_base + static_cast<uint32_t>(as * BN + chalf * COLS_PER_WARP) +
+                                   (static_cast<uint32_t>(lq * 32) << 16);
 
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
@@ -205,17 +238,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 {
                     uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
                     uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
-                    tmem_ld_32x32(t_acc + c * CH, r0);
-                    tmem_ld_32x32(t_acc + c * CH + 32, r1);
+                    tmem_ld_32x32(t_acc + c * 64, r0);
+                    tmem_ld_32x32(t_acc + c * 64 + 32, r1);
                     tmem_ld_wait();
                 }
                 if (c == NCH - 1) {
-                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                    // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[as]);
                 }
-                const int ncol0 = n0 + c * CH;
+                const int ncol0 = n0 + c * 64;
+                if (!rows_live || ncol0 >= args.n_valid) continue;
                 if (args.rope != nullptr && ncol0 < args.rope_cols) {
                     const int pos = (q_warp0 + lane) % args.rope_seq;
                     const float2* tab = args.rope + static_cast<size_t>(pos) * 32;
@@ -228,55 +262,129 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         r[j + 32] = __float_as_uint(x2 * cs.x + x1 * cs.y);
                     }
                 }
-                // registers (thread = row) -> swizzled smem (conflict-free float4 stores)
+                if (args.bias != nullptr) {
+                    const float4* b4 = reinterpret_cast<const float4*>(args.bias + ncol0);
 #pragma unroll
-                for (int c4 = 0; c4 < 16; ++c4) {
-                    float4 v = make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]),
-                                           __uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
-                    *reinterpret_cast<float4*>(stg + lane * 64 + ((c4 ^ (lane & 7)) << 2)) = v;
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + b.x);
+                        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y);
+                        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z);
+                        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w);
+                    }
                 }
-                __syncwarp();
-                // smem -> global, lane = column pair, coalesced rows
-                const int n = ncol0 + 2 * lane;
-                const bool n_ok = n < args.n_valid;      // n_valid is even
-                float b0 = 0.f, b1 = 0.f;
-                if (args.bias != nullptr && n_ok) {
-                    b0 = __ldg(args.bias + n);
-                    b1 = __ldg(args.bias + n + 1);
-                }
-                const int phase = n / args.phase_w;
+                if (use_tma) {
+                    // ---------------- fp32 output (+ residual): two [32 x 32] fp32 sub-tiles
+                    if (args.has_out_f32) {
+#pragma unroll
+                        for (int sp = 0; sp < 2; ++sp) {
+                            const int ncol = ncol0 + sp * 32;
+                            if (ncol < args.n_valid) {
+                                if (has_res) {
+                                    mbar_wait(my_rbar, rph);
+                                    rph ^= 1;
+#pragma unroll
+                                    for (int c4 = 0; c4 < 8; ++c4) {
+                                        const float4 v = *reinterpret_cast<const float4*>(my_row + ((c4 ^ sw) << 4));
+                                        const int b = sp * 32 + 4 * c4;
+                                        r[b] = __float_as_uint(__uint_as_float(r[b]) + v.x);
+                                        r[b + 1] = __float_as_uint(__uint_as_float(r[b + 1]) + v.y);
+                                        r[b + 2] = __float_as_uint(__uint_as_float(r[b + 2]) + v.z);
+                                        r[b + 3] = __float_as_uint(__uint_as_float(r[b + 3]) + v.w);
+                                    }
+                                } else if (lane == 0) {
+                                    bulk_wait_read0();              // previous TMA store has finished reading the buffer
+                                }
+                                __syncwarp();
+#pragma unroll
+                                for (int c4 = 0; c4 < 8; ++c4) {
+                                    const int b = sp * 32 + 4 * c4;
+                                    *reinterpret_cast<uint4*>(my_row + ((c4 ^ sw) << 4)) = make_uint4(r[b], r[b + 1], r[b + 2], r[b + 3]);
+                                }
+                                fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_3d(&args.tmOutF, buf, ncol, q_warp0, z);
+                                    bulk_commit();
+                                    if (has_res && sp == 0 && ncol + 32 < args.n_valid) {
+                                        bulk_wait_read0();
+                                        mbar_expect_tx(my_rbar, GEMM_EPI_BUF_BYTES);
+                                        tma_load_3d(buf, &args.tmRes, my_rbar, ncol + 32, q_warp0, z);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    // ---------------- 16-bit output: one [32 x 64] sub-tile
+                    if (args.has_out_h) {
+                        uint32_t pk[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float o0 = __uint_as_float(r[2 * j]), o1 = __uint_as_float(r[2 * j + 1]);
+                            if (args.act_h == ACT_GELU) { o0 = gelu_fast(o0); o1 = gelu_fast(o1); }
+                            else if (args.act_h == ACT_LRELU) { o0 = lrelu(o0, args.slope); o1 = lrelu(o1, args.slope); }
+                            pk[j] = pack_h2(o0, o1, args.h_is_fp16);
+                        }
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4)
+                            *reinterpret_cast<uint4*>(my_row + ((c4 ^ sw) << 4)) =
+                                make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&args.tmOutH, buf, ncol0, q_warp0, z);
+                            bulk_commit();
+                        }
+                    }
+                    // residual sub-tile of the next chunk's first sub-pass
+                    if (has_res && lane == 0 && c + 1 < NCH && ncol0 + 64 < args.n_valid) {
+                        bulk_wait_read0();
+                        mbar_expect_tx(my_rbar, GEMM_EPI_BUF_BYTES);
+                        tma_load_3d(buf, &args.tmRes, my_rbar, ncol0 + 64, q_warp0, z);
+                    }
+                } else {
+                    // ---------------- scatter path (ConvTranspose1d): smem transpose, lane = column, per-element stores
+                    const float* stg = reinterpret_cast<const float*>(buf);
+#pragma unroll
+                    for (int sp = 0; sp < 2; ++sp) {
+                        __syncwarp();
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const int b = sp * 32 + 4 * c4;
+                            *reinterpret_cast<uint4*>(my_row + ((c4 ^ sw) << 4)) = make_uint4(r[b], r[b + 1], r[b + 2], r[b + 3]);
+                        }
+                        __syncwarp();
+                        const int n = ncol0 + sp * 32 + lane;
+                        if (n < args.n_valid) {
+                            const int phase = n / args.phase_w;
+                            const long long base = static_cast<long long>(z) * args.out_zs + args.out_off + n;
 #pragma unroll 4
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int q = q_warp0 + rr;
-                    const int t = args.up_s * q + phase - args.up_p;
-                    if (!n_ok || t < 0 || t >= args.t_out) continue;
-                    const float2 a = *reinterpret_cast<const float2*>(
-                        stg + rr * 64 + ((((lane >> 1) ^ (rr & 7)) << 2) | ((lane & 1) << 1)));
-                    float v0 = a.x + b0, v1 = a.y + b1;
-                    const long long off = static_cast<long long>(z) * args.out_zs + static_cast<long long>(q) * args.out_rs +
-                                          n + args.out_off;
-                    if (args.residual != nullptr) {
-                        const float2 rsd = *reinterpret_cast<const float2*>(args.residual + off);
-                        v0 += rsd.x;
-                        v1 += rsd.y;
+                            for (int rr = 0; rr < 32; ++rr) {
+                                const int q = q_warp0 + rr;
+                                const int t = args.up_s * q + phase - args.up_p;
+                                if (t < 0 || t >= args.t_out) continue;
+                                const float v = stg[rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)];
+                                const long long off = base + static_cast<long long>(q) * args.out_rs;
+                                if (args.out_f32 != nullptr) args.out_f32[off] = v;
+                                if (args.out_h != nullptr) {
+                                    float o = v;
+                                    if (args.act_h == ACT_GELU) o = gelu_fast(o);
+                                    else if (args.act_h == ACT_LRELU) o = lrelu(o, args.slope);
+                                    static_cast<uint16_t*>(args.out_h)[off] =
+                                        args.h_is_fp16 ? __half_as_ushort(__float2half_rn(o))
+                                                       : __bfloat16_as_ushort(__float2bfloat16(o));
+                                }
+                            }
+                        }
                     }
-                    if (args.out_f32 != nullptr) {
-                        float o0 = v0, o1 = v1;
-                        if (args.act_f32 == ACT_TANH) { o0 = tanhf(o0); o1 = tanhf(o1); }
-                        *reinterpret_cast<float2*>(args.out_f32 + off) = make_float2(o0, o1);
-                    }
-                    if (args.out_h != nullptr) {
-                        float o0 = v0, o1 = v1;
-                        if (args.act_h == ACT_GELU) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); }
-                        else if (args.act_h == ACT_LRELU) { o0 = lrelu(o0, args.slope); o1 = lrelu(o1, args.slope); }
-                        *reinterpret_cast<uint32_t*>(static_cast<uint16_t*>(args.out_h) + off) =
-                            pack_h2(o0, o1, args.h_is_fp16);
-                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
+        if (lane == 0) bulk_wait_all();      // smem must stay valid until every bulk store has been read out
     }
 
     tc_fence_before();

@@ -112,13 +112,14 @@ inline int hifi_conv_op(const covo_hifigan* h, GemmOp& op, const void* act, int 
         op.args.tap_row[j] = j * dil - pad;
         op.args.tap_z[j] = 0;
     }
-    op.args.n_valid = c_out_pad;
-    op.args.out_zs = static_cast<long long>(T) * c_out_pad;
-    op.args.out_rs = c_out_pad;
-    op.args.t_out = T;
     op.args.bias = bias.as<float>();
-    op.args.h_is_fp16 = h->is_fp16;
+    op.cat = PC_GEMM_VOC;
     return COVO_OK;
+}
+inline int hifi_conv_out(const covo_hifigan* h, GemmOp& op, float* out_f32, const float* residual, void* out_h, int T, int B,
+                         int c_out_pad) {
+    return gemm_set_outputs(op, out_f32, residual, out_h, c_out_pad, T, B, c_out_pad, static_cast<long long>(T) * c_out_pad,
+                            h->is_fp16);
 }
 inline double conv_flops(int B, int T, int cin, int cout, int k) { return 2.0 * B * T * static_cast<double>(cin) * cout * k; }
 
@@ -131,7 +132,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
     COVO_TRY(w.get("conv_pre.b", DT_F32, &tb));
     const int c0p = pad64(hifi_chan(c, -1));
     COVO_TRY(hifi_conv_op(h, p.pre, p.mel_tc, h->mel_pad, p.T, p.B, tw, tb, c0p, 7, 1));
-    p.pre.args.out_h = p.pre_act;                               // x = lrelu(conv_pre(mel)) (models.py:101-103)
+    COVO_TRY(hifi_conv_out(h, p.pre, nullptr, nullptr, p.pre_act, p.T, p.B, c0p));    // x = lrelu(conv_pre(mel)) (models.py:101-103)
     p.pre.args.act_h = ACT_LRELU;
     p.pre.args.slope = 0.1f;
     p.pre.flops = conv_flops(p.B, p.T, c.num_mels, hifi_chan(c, -1), 7);
@@ -154,6 +155,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
                 op.args.tap_row[j] = -j;
                 op.args.tap_z[j] = 0;
             }
+            op.args.scatter = 1;
             op.args.n_valid = s.stride * s.c_out_pad;
             op.args.out_zs = static_cast<long long>(s.t_out) * s.c_out_pad;
             op.args.out_rs = static_cast<long long>(s.stride) * s.c_out_pad;
@@ -169,6 +171,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
             op.args.slope = 0.1f;
             op.args.h_is_fp16 = h->is_fp16;
             op.flops = conv_flops(p.B, s.t_in, hifi_chan(c, i - 1), s.c_out, s.ksize);
+            op.cat = PC_GEMM_VOC;
             ++p.launches;
         }
         // ---- resblocks
@@ -188,7 +191,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
                     COVO_TRY(w.get(n1 + ".b", DT_F32, &tb));
                     GemmOp o1;
                     COVO_TRY(hifi_conv_op(h, o1, in1, s.c_out_pad, s.t_out, p.B, tw, tb, s.c_out_pad, k, d));
-                    o1.args.out_h = s.hr[j];
+                    COVO_TRY(hifi_conv_out(h, o1, nullptr, nullptr, s.hr[j], s.t_out, p.B, s.c_out_pad));
                     o1.args.act_h = ACT_LRELU;
                     o1.flops = conv_flops(p.B, s.t_out, s.c_out, s.c_out, k);
                     s.convs.push_back(o1);
@@ -196,12 +199,9 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
                     COVO_TRY(w.get(n2 + ".b", DT_F32, &tb));
                     GemmOp o2;
                     COVO_TRY(hifi_conv_op(h, o2, s.hr[j], s.c_out_pad, s.t_out, p.B, tw, tb, s.c_out_pad, k, 1));
-                    o2.args.residual = res;
-                    o2.args.out_f32 = s.xr[j];
-                    if (m + 1 < c.num_dilations) {
-                        o2.args.out_h = s.ar[j];
-                        o2.args.act_h = ACT_LRELU;
-                    }
+                    COVO_TRY(hifi_conv_out(h, o2, s.xr[j], res, (m + 1 < c.num_dilations) ? s.ar[j] : nullptr, s.t_out, p.B,
+                                           s.c_out_pad));
+                    o2.args.act_h = ACT_LRELU;
                     o2.flops = conv_flops(p.B, s.t_out, s.c_out, s.c_out, k);
                     s.convs.push_back(o2);
                 } else {
@@ -211,12 +211,9 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
                     COVO_TRY(w.get(n1 + ".b", DT_F32, &tb));
                     GemmOp o1;
                     COVO_TRY(hifi_conv_op(h, o1, in1, s.c_out_pad, s.t_out, p.B, tw, tb, s.c_out_pad, k, d));
-                    o1.args.residual = res;
-                    o1.args.out_f32 = s.xr[j];
-                    if (m + 1 < c.num_dilations) {
-                        o1.args.out_h = s.ar[j];
-                        o1.args.act_h = ACT_LRELU;
-                    }
+                    COVO_TRY(hifi_conv_out(h, o1, s.xr[j], res, (m + 1 < c.num_dilations) ? s.ar[j] : nullptr, s.t_out, p.B,
+                                           s.c_out_pad));
+                    o1.args.act_h = ACT_LRELU;
                     o1.flops = conv_flops(p.B, s.t_out, s.c_out, s.c_out, k);
                     s.convs.push_back(o1);
                 }

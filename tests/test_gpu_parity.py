@@ -183,7 +183,9 @@ def test_hifigan_matches_reference(dev, vocoder):
         host = (wav.reshape(-1) * 32768.0).cpu().numpy().astype("int16")
         assert np.array_equal(i16, host)
         ri = (ref.reshape(-1) * 32768.0).numpy().astype("int16").astype(np.int64)
-        close = np.abs(i16.astype(np.int64) - ri) <= np.maximum(4, np.abs(ri) / 64)
+        # 16-bit operands give additive noise ~8e-4 of the signal RMS (about -62 dB), not a per-sample relative error
+        rms = float(np.sqrt(np.mean(ri.astype(np.float64) ** 2)))
+        close = np.abs(i16.astype(np.int64) - ri) <= max(2.0, 4e-3 * rms)
         assert close.mean() > 0.99
         f16 = gen(mel.to(dev), out_dtype="f16")
         assert torch.equal(f16, wav.half())
