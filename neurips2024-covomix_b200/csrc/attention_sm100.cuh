@@ -3,29 +3,32 @@
 // Replaces Attend.forward's einsum/softmax/einsum (covomix/covomix_model/attend.py:110-124), which
 // materialises the [B,H,N,N] fp32 score tensor in HBM; here scores never leave the SM.
 //
-// One CTA = one (sequence b, head h, 128-query tile).  Q/K/V tiles are TMA-loaded straight out of
-// the to_qkv GEMM's [B*N, 3*H*64] bf16 output (3-D tensor map: column, position, sequence; rows
-// past the end of a sequence are zero-filled by TMA and masked to -inf in the softmax).
-//   warp 0   : TMA producer (Q once, then a 2-stage ring of K and V tiles of 128 keys)
-//   warp 1   : tcgen05.mma issuer:  S_j = Q K_j^T  (M128 x N128 x K64, both K-major, into TMEM),
-//              O_j = P_j V_j (M128 x N64 x K128, A = P from smem, B = V MN-major, into TMEM)
-//   warps 2-5: softmax, one query row per thread (TMEM lane == row, so row max / row sum need no
-//              shuffles): S_j from TMEM -> running max, exp2, row sum -> P_j as bf16 into 128B-swizzled
-//              smem (the A operand of the PV MMA) -> O_{j-1} from TMEM, rescale-and-accumulate in
-//              registers.  S, P and O are double-buffered so the MMAs of tile j+1 overlap the softmax
-//              of tile j.
+// One CTA = one (sequence b, head h, 256-query tile) = two 128-query groups A and B that share every
+// K/V tile and ping-pong on the tensor pipe: while the softmax warps of one group work on S_j, the
+// MMAs of the other group run.  Q/K/V tiles are TMA-loaded straight out of the to_qkv GEMM's
+// [B*N, 3*H*64] bf16 output (3-D tensor map: column, position, sequence; rows past the end of a
+// sequence are zero-filled by TMA and masked to -inf in the softmax).
+//   warp 0      : TMA producer (both Q tiles once, then a 2-stage ring of K and V tiles of 128 keys)
+//   warp 1      : tcgen05.mma issuer:  S_g = Q_g K_j^T (M128 x N128 x K64, K-major operands, into TMEM),
+//                 O_g = P_g V_j (M128 x N64 x K128, A = P from smem, B = V MN-major, into TMEM);
+//                 S_g(j) is issued before P_g(j-1) V_{j-1} so the pipe always has work queued
+//   warps 4-7   : softmax group A, warps 8-11: group B; one query row per thread (TMEM lane == row, so
+//                 row max / row sum need no shuffles): S_j from TMEM into registers (buffer released at
+//                 once) -> running max, exp2, row sum -> P_j as bf16 into 128B-swizzled smem (the A
+//                 operand of the PV MMA) -> O_{j-1} from TMEM, rescale-and-accumulate in registers.
+// Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 40, softmax warpgroups 232).
 #pragma once
 #include "ptx.cuh"
 
 namespace covo {
 
-constexpr int ATT_BM = 128;      // queries per CTA
+constexpr int ATT_BM = 256;      // queries per CTA (two groups of 128)
 constexpr int ATT_BN = 128;      // keys per iteration
 constexpr int ATT_D = 64;        // dim_head
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 384; // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1, 2: softmax A, B
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                 // 16 KB: one [128 x 64] bf16 tile
-constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;             // 32 KB
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES /*Q*/ + 2 * ATT_TILE_BYTES /*K*/ + 2 * ATT_TILE_BYTES /*V*/ +
+constexpr int ATT_P_BYTES = 128 * ATT_BN * 2;                // 32 KB
+constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES /*Q*/ + 2 * ATT_TILE_BYTES /*K*/ + 2 * ATT_TILE_BYTES /*V*/ +
                                2 * ATT_P_BYTES + 256 + 1024;
 constexpr int ATT_TMEM_COLS = 512;                           // S: 2 x 128, O: 2 x 64 (power of two >= 384)
 
@@ -44,33 +47,38 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {   // sm_100 three-input max: one FMNMX3 instead of two FMNMX
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + ATT_TILE_BYTES;            // 2 stages
+    uint8_t* sQ = smem;                           // 2 groups
+    uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;        // 2 stages
     uint8_t* sV = sK + 2 * ATT_TILE_BYTES;        // 2 stages
-    uint8_t* sP = sV + 2 * ATT_TILE_BYTES;        // 2 buffers
+    uint8_t* sP = sV + 2 * ATT_TILE_BYTES;        // 2 groups
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;    // [2]
-    uint64_t* k_empty = bars + 3;   // [2]
-    uint64_t* v_full = bars + 5;    // [2]
-    uint64_t* v_empty = bars + 7;   // [2]
-    uint64_t* s_full = bars + 9;    // [2]  MMA -> softmax
-    uint64_t* s_free = bars + 11;   // [2]  softmax -> MMA
-    uint64_t* p_full = bars + 13;   // [2]  softmax -> MMA
-    uint64_t* p_free = bars + 15;   // [2]  MMA -> softmax
-    uint64_t* o_full = bars + 17;   // [2]  MMA -> softmax
-    uint64_t* o_free = bars + 19;   // [2]  softmax -> MMA
+    uint64_t* k_full = bars + 1;    // [2 stages]
+    uint64_t* k_empty = bars + 3;
+    uint64_t* v_full = bars + 5;
+    uint64_t* v_empty = bars + 7;
+    uint64_t* s_full = bars + 9;    // [2 groups]  MMA -> softmax
+    uint64_t* s_free = bars + 11;   //             softmax -> MMA
+    uint64_t* p_full = bars + 13;   //             softmax -> MMA
+    uint64_t* p_free = bars + 15;   //             MMA -> softmax
+    uint64_t* o_full = bars + 17;   //             MMA -> softmax
+    uint64_t* o_free = bars + 19;   //             softmax -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int q_tile = blockIdx.x;
     const int head = blockIdx.y;
     const int seq = blockIdx.z;
-    const int q0 = q_tile * ATT_BM;
+    const int q0 = blockIdx.x * ATT_BM;
     const int n_kv = (args.N + ATT_BN - 1) / ATT_BN;
 
     if (warp == 0 && lane == 0) {
@@ -98,14 +106,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base;            // + buf * 128
-    const uint32_t tmem_O = tmem_base + 256;      // + buf * 64
+    const uint32_t tmem_S = tmem_base;            // + group * 128
+    const uint32_t tmem_O = tmem_base + 256;      // + group * 64
 
-    if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
-            mbar_expect_tx(q_full, ATT_TILE_BYTES);
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0 && lane == 0) {
+            // ===================================================== TMA producer
+            mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
             tma_load_3d(sQ, &args.tmQKV, q_full, head * ATT_D, q0, seq);
+            tma_load_3d(sQ + ATT_TILE_BYTES, &args.tmQKV, q_full, head * ATT_D, q0 + 128, seq);
             for (int j = 0; j < n_kv; ++j) {
                 const int st = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
@@ -117,57 +127,63 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 tma_load_3d(sV + st * ATT_TILE_BYTES, &args.tmQKV, &v_full[st], 2 * args.inner + head * ATT_D, j * ATT_BN,
                             seq);
             }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_f16(ATT_BM, ATT_BN, 1, 0, 0);   // Q K^T : both K-major
-            constexpr uint32_t idesc_o = make_idesc_f16(ATT_BM, ATT_D, 1, 0, 1);    // P V   : V is MN-major
-            const uint32_t aQ = smem_u32(sQ);
-            auto issue_S = [&](int j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&k_full[st], ph);
-                mbar_wait(&s_free[st], ph ^ 1);
-                tc_fence_after();
-                const uint32_t aK = smem_u32(sK + st * ATT_TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < ATT_D / 16; ++k) {
-                    umma_f16(tmem_S + st * ATT_BN, smem_desc_sw128(aQ + k * 32, 1024, 16),
-                             smem_desc_sw128(aK + k * 32, 1024, 16), idesc_s, k != 0);
-                }
-                umma_commit(&k_empty[st]);
-                umma_commit(&s_full[st]);
-            };
+        } else if (warp == 1 && lane == 0) {
+            // ===================================================== MMA issuer
+            constexpr uint32_t idesc_s = make_idesc_f16(128, ATT_BN, 1, 0, 0);   // Q K^T : both K-major
+            constexpr uint32_t idesc_o = make_idesc_f16(128, ATT_D, 1, 0, 1);    // P V   : V is MN-major
             mbar_wait(q_full, 0);
-            issue_S(0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) issue_S(j + 1);
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&v_full[st], ph);
-                mbar_wait(&p_full[st], ph);
-                mbar_wait(&o_free[st], ph ^ 1);
-                tc_fence_after();
-                const uint32_t aP = smem_u32(sP + st * ATT_P_BYTES);
-                const uint32_t aV = smem_u32(sV + st * ATT_TILE_BYTES);
+            for (int j = 0; j <= n_kv; ++j) {
+                if (j < n_kv) {
+                    const int st = j & 1;
+                    mbar_wait(&k_full[st], (j >> 1) & 1);
+                    const uint32_t aK = smem_u32(sK + st * ATT_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < ATT_BN / 16; ++k) {
-                    // A = P: K-major, two 64-key chunks of [128 x 128 B]; B = V: MN-major, 16 keys = 2048 B apart
-                    const uint64_t da = smem_desc_sw128(aP + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 16);
-                    const uint64_t db = smem_desc_sw128(aV + k * 2048, 1024, ATT_TILE_BYTES);
-                    umma_f16(tmem_O + st * ATT_D, da, db, idesc_o, k != 0);
+                    for (int g = 0; g < 2; ++g) {
+                        mbar_wait(&s_free[g], (j & 1) ^ 1);        // softmax has pulled S_g(j-1) into registers
+                        tc_fence_after();
+                        const uint32_t aQ = smem_u32(sQ + g * ATT_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < ATT_D / 16; ++k)
+                            umma_f16(tmem_S + g * ATT_BN, smem_desc_sw128(aQ + k * 32, 1024, 16),
+                                     smem_desc_sw128(aK + k * 32, 1024, 16), idesc_s, k != 0);
+                        umma_commit(&s_full[g]);
+                    }
+                    umma_commit(&k_empty[st]);
                 }
-                umma_commit(&v_empty[st]);
-                umma_commit(&p_free[st]);
-                umma_commit(&o_full[st]);
+                if (j >= 1) {
+                    const int jj = j - 1;
+                    const int st = jj & 1;
+                    mbar_wait(&v_full[st], (jj >> 1) & 1);
+                    const uint32_t aV = smem_u32(sV + st * ATT_TILE_BYTES);
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        mbar_wait(&p_full[g], jj & 1);
+                        mbar_wait(&o_free[g], (jj & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t aP = smem_u32(sP + g * ATT_P_BYTES);
+#pragma unroll
+                        for (int k = 0; k < ATT_BN / 16; ++k) {
+                            // A = P: K-major, two 64-key chunks of [128 x 128 B]; B = V: MN-major, 16 keys = 2048 B apart
+                            const uint64_t da = smem_desc_sw128(aP + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 16);
+                            const uint64_t db = smem_desc_sw128(aV + k * 2048, 1024, ATT_TILE_BYTES);
+                            umma_f16(tmem_O + g * ATT_D, da, db, idesc_o, k != 0);
+                        }
+                        umma_commit(&p_free[g]);
+                        umma_commit(&o_full[g]);
+                    }
+                    umma_commit(&v_empty[st]);
+                }
             }
         }
     } else {
-        // ===================================================== softmax warps: thread == query row
-        const int lq = warp & 3;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ===================================================== softmax warpgroups: thread == query row
+        const int g = (warp - 4) >> 2;                 // 0: group A (warps 4-7), 1: group B (warps 8-11)
+        const int lq = warp & 3;                       // TMEM lane quarter
         const int row = lq * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lq * 32) << 16;
+        const uint32_t tS = tmem_S + g * ATT_BN + lane_addr;
+        const uint32_t tO = tmem_O + g * ATT_D + lane_addr;
         const float c = args.scale_log2e;
         float m_run = -INFINITY;     // running max of raw scores
         float l_run = 0.f;           // running sum of exp
@@ -175,85 +191,96 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         float acc[ATT_D];
 #pragma unroll
         for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
+        uint8_t* prow = sP + g * ATT_P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+        const int sw = row & 7;
 
         auto accumulate_O = [&](int j, float alpha) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            mbar_wait(&o_full[st], ph);
+            mbar_wait(&o_full[g], j & 1);
             tc_fence_after();
             uint32_t o[64];
             uint32_t (&o0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
             uint32_t (&o1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[32]);
-            tmem_ld_32x32(tmem_O + st * ATT_D + lane_addr, o0);
-            tmem_ld_32x32(tmem_O + st * ATT_D + 32 + lane_addr, o1);
+            tmem_ld_32x32(tO, o0);
+            tmem_ld_32x32(tO + 32, o1);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[st]);
+            if (lane == 0) mbar_arrive(&o_free[g]);
 #pragma unroll
-            for (int d = 0; d < ATT_D; ++d) acc[d] = acc[d] * alpha + __uint_as_float(o[d]);
+            for (int d = 0; d < ATT_D; ++d) acc[d] = fmaf(acc[d], alpha, __uint_as_float(o[d]));
         };
 
         for (int j = 0; j < n_kv; ++j) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            mbar_wait(&s_full[st], ph);
+            mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
-            const int kv_valid = args.N - j * ATT_BN;      // keys >= kv_valid are padding (last tile only)
-            // pass 1: row max over the 128 scores of this tile
-            float m_tile = -INFINITY;
-#pragma unroll 1
-            for (int cb = 0; cb < ATT_BN / 32; ++cb) {
-                uint32_t s[32];
-                tmem_ld_32x32(tmem_S + st * ATT_BN + cb * 32 + lane_addr, s);
+            uint32_t s[128];
+            {
+                uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+                uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+                uint32_t (&s2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[64]);
+                uint32_t (&s3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[96]);
+                tmem_ld_32x32(tS, s0);
+                tmem_ld_32x32(tS + 32, s1);
+                tmem_ld_32x32(tS + 64, s2);
+                tmem_ld_32x32(tS + 96, s3);
                 tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = (cb * 32 + i < kv_valid) ? __uint_as_float(s[i]) : -INFINITY;
-                    m_tile = fmaxf(m_tile, v);
-                }
             }
-            const float m_new = fmaxf(m_run, m_tile);
+            // S is in registers: the MMA warp may overwrite the buffer with S(j+1)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g]);
+
+            const int kv_valid = args.N - j * ATT_BN;      // keys >= kv_valid are padding (last tile only)
+            if (kv_valid < ATT_BN) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+            }
+            // row max: 4 independent chains of three-input max
+            float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+                  mx3 = __uint_as_float(s[3]);
+#pragma unroll
+            for (int i = 4; i + 7 < 128; i += 8) {
+                mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+                mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+                mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+            }
+            mx0 = fmax3(mx0, __uint_as_float(s[124]), __uint_as_float(s[125]));
+            mx1 = fmax3(mx1, __uint_as_float(s[126]), __uint_as_float(s[127]));
+            const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
             const float alpha = ex2_approx((m_run - m_new) * c);    // first tile: exp2(-inf) = 0
             const float mc = m_new * c;
-            // P buffer must have been consumed by the PV MMA two tiles ago
-            mbar_wait(&p_free[st], ph ^ 1);
-            // pass 2: p = exp2(s*c - m*c), row sum, bf16 -> swizzled smem
-            float l_tile = 0.f;
-            uint8_t* prow = sP + st * ATT_P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll 1
-            for (int cb = 0; cb < ATT_BN / 32; ++cb) {
-                uint32_t s[32];
-                tmem_ld_32x32(tmem_S + st * ATT_BN + cb * 32 + lane_addr, s);
-                tmem_ld_wait();
-                uint32_t pk[16];
+            // p = exp2(s*c - m*c) -> bf16 pairs; the row sum is taken in fp32 before rounding
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (cb * 32 + i < kv_valid) ? ex2_approx(__uint_as_float(s[i]) * c - mc) : 0.f;
-                    float p1 = (cb * 32 + i + 1 < kv_valid) ? ex2_approx(__uint_as_float(s[i + 1]) * c - mc) : 0.f;
-                    __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-                    // the row sum uses the rounded probabilities, i.e. exactly what the PV MMA multiplies
-                    l_tile += __low2float(h) + __high2float(h);
-                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                // 32 keys = 64 B = four 16-B pieces; key chunk kc = cb/2, piece index within the 128-B row = (cb&1)*4 + t
-                uint8_t* pchunk = prow + (cb >> 1) * ATT_TILE_BYTES;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int piece = ((cb & 1) * 4 + t) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(pchunk + piece * 16) =
-                        make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-                }
+            for (int i = 0; i < 128; i += 4) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, -mc));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, -mc));
+                const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), c, -mc));
+                const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), c, -mc));
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1);
+                const __nv_bfloat162 h23 = __floats2bfloat162_rn(p2, p3);
+                l0 += p0;
+                l1 += p1;
+                l2 += p2;
+                l3 += p3;
+                s[i >> 1] = *reinterpret_cast<const uint32_t*>(&h01);          // pack in place: s[0..63] = P
+                s[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
             }
-            // S buffer fully read; P written: publish both
-            tc_fence_before();
+            // P buffer must have been consumed by the PV MMA of the previous tile
+            mbar_wait(&p_free[g], (j & 1) ^ 1);
+            // 128 keys = two 64-key chunks (128 B each per row); 16-B piece t of chunk kc at ((t ^ (row&7)) * 16)
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    *reinterpret_cast<uint4*>(prow + kc * ATT_TILE_BYTES + ((t ^ sw) << 4)) =
+                        make_uint4(s[kc * 32 + 4 * t], s[kc * 32 + 4 * t + 1], s[kc * 32 + 4 * t + 2], s[kc * 32 + 4 * t + 3]);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&s_free[st]);
-                mbar_arrive(&p_full[st]);
-            }
-            l_run = l_run * alpha + l_tile;
+            if (lane == 0) mbar_arrive(&p_full[g]);
+            l_run = fmaf(l_run, alpha, (l0 + l1) + (l2 + l3));
             m_run = m_new;
             // deferred accumulation of the previous tile's O (its MMA ran while we did this tile's softmax)
             if (j > 0) accumulate_O(j - 1, alpha_prev);
@@ -261,7 +288,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         }
         accumulate_O(n_kv - 1, alpha_prev);
 
-        const int qpos = q0 + row;
+        const int qpos = q0 + g * 128 + row;
         if (qpos < args.N) {
             const float inv = 1.0f / l_run;
             __nv_bfloat16* dst = args.out + (static_cast<size_t>(seq) * args.N + qpos) * args.inner + head * ATT_D;
