@@ -16,7 +16,7 @@
 //                 row max / row sum need no shuffles): S_j from TMEM into registers (buffer released at
 //                 once) -> running max, exp2, row sum -> P_j as bf16 into 128B-swizzled smem (the A
 //                 operand of the PV MMA) -> O_{j-1} from TMEM, rescale-and-accumulate in registers.
-// Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 40, softmax warpgroups 232).
+// Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 56, softmax warpgroups 224; the pool is exactly what warpgroup 0 releases).
 #pragma once
 #include "ptx.cuh"
 
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     const uint32_t tmem_O = tmem_base + 256;      // + group * 64
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 0 && lane == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0 && elect_one()) {
             // ===================================================== TMA producer
             mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
             tma_load_3d(sQ, &args.tmQKV, q_full, head * ATT_D, q0, seq);
@@ -127,25 +127,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 tma_load_3d(sV + st * ATT_TILE_BYTES, &args.tmQKV, &v_full[st], 2 * args.inner + head * ATT_D, j * ATT_BN,
                             seq);
             }
-        } else if (warp == 1 && lane == 0) {
-            // ===================================================== MMA issuer
+        } else if (warp == 1 && elect_one()) {
+            // ===================================================== MMA issuer (elect.sync: ptxas keeps operands in uniform registers)
             constexpr uint32_t idesc_s = make_idesc_f16(128, ATT_BN, 1, 0, 0);   // Q K^T : both K-major
             constexpr uint32_t idesc_o = make_idesc_f16(128, ATT_D, 1, 0, 1);    // P V   : V is MN-major
+            // Descriptors are built once; per MMA only the 14-bit start-address field is advanced (one add), so the
+            // single issuing thread never becomes the bottleneck (24 MMAs per key tile).
+            uint64_t dQ[2], dK[2], dP[2], dV[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                dQ[i] = smem_desc_sw128(smem_u32(sQ + i * ATT_TILE_BYTES), 1024, 16);
+                dK[i] = smem_desc_sw128(smem_u32(sK + i * ATT_TILE_BYTES), 1024, 16);
+                dP[i] = smem_desc_sw128(smem_u32(sP + i * ATT_P_BYTES), 1024, 16);
+                dV[i] = smem_desc_sw128(smem_u32(sV + i * ATT_TILE_BYTES), 1024, ATT_TILE_BYTES);
+            }
             mbar_wait(q_full, 0);
             for (int j = 0; j <= n_kv; ++j) {
                 if (j < n_kv) {
                     const int st = j & 1;
                     mbar_wait(&k_full[st], (j >> 1) & 1);
-                    const uint32_t aK = smem_u32(sK + st * ATT_TILE_BYTES);
+                    const uint64_t bK = st ? dK[1] : dK[0];
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         mbar_wait(&s_free[g], (j & 1) ^ 1);        // softmax has pulled S_g(j-1) into registers
                         tc_fence_after();
-                        const uint32_t aQ = smem_u32(sQ + g * ATT_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < ATT_D / 16; ++k)
-                            umma_f16(tmem_S + g * ATT_BN, smem_desc_sw128(aQ + k * 32, 1024, 16),
-                                     smem_desc_sw128(aK + k * 32, 1024, 16), idesc_s, k != 0);
+                            umma_f16(tmem_S + g * ATT_BN, desc_advance(dQ[g], k * 32), desc_advance(bK, k * 32), idesc_s, k != 0);
                         umma_commit(&s_full[g]);
                     }
                     umma_commit(&k_empty[st]);
@@ -154,19 +162,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                     const int jj = j - 1;
                     const int st = jj & 1;
                     mbar_wait(&v_full[st], (jj >> 1) & 1);
-                    const uint32_t aV = smem_u32(sV + st * ATT_TILE_BYTES);
+                    const uint64_t bV = st ? dV[1] : dV[0];
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         mbar_wait(&p_full[g], jj & 1);
                         mbar_wait(&o_free[g], (jj & 1) ^ 1);
                         tc_fence_after();
-                        const uint32_t aP = smem_u32(sP + g * ATT_P_BYTES);
 #pragma unroll
                         for (int k = 0; k < ATT_BN / 16; ++k) {
                             // A = P: K-major, two 64-key chunks of [128 x 128 B]; B = V: MN-major, 16 keys = 2048 B apart
-                            const uint64_t da = smem_desc_sw128(aP + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 16);
-                            const uint64_t db = smem_desc_sw128(aV + k * 2048, 1024, ATT_TILE_BYTES);
-                            umma_f16(tmem_O + g * ATT_D, da, db, idesc_o, k != 0);
+                            umma_f16(tmem_O + g * ATT_D, desc_advance(dP[g], (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32),
+                                     desc_advance(bV, k * 2048), idesc_o, k != 0);
                         }
                         umma_commit(&p_free[g]);
                         umma_commit(&o_full[g]);
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================================================== softmax warpgroups: thread == query row
         const int g = (warp - 4) >> 2;                 // 0: group A (warps 4-7), 1: group B (warps 8-11)
         const int lq = warp & 3;                       // TMEM lane quarter
@@ -193,6 +199,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
         uint8_t* prow = sP + g * ATT_P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
         const int sw = row & 7;
+        const uint32_t prow_s = smem_u32(prow);
 
         auto accumulate_O = [&](int j, float alpha) {
             mbar_wait(&o_full[g], j & 1);
@@ -275,8 +282,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
-                    *reinterpret_cast<uint4*>(prow + kc * ATT_TILE_BYTES + ((t ^ sw) << 4)) =
-                        make_uint4(s[kc * 32 + 4 * t], s[kc * 32 + 4 * t + 1], s[kc * 32 + 4 * t + 2], s[kc * 32 + 4 * t + 3]);
+                    sts128(prow_s + kc * ATT_TILE_BYTES + ((t ^ sw) << 4), s[kc * 32 + 4 * t], s[kc * 32 + 4 * t + 1],
+                           s[kc * 32 + 4 * t + 2], s[kc * 32 + 4 * t + 3]);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g]);

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
     if (warp == 0) {
         // ===================================================== TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -165,9 +165,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================== MMA issuer (elect.sync: ptxas keeps operands in uniform registers)
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, AB_FMT, 0, 0);
+            // descriptors of stage 0, built once; per stage / per K16 step only the start-address field is advanced
+            const uint64_t dA0 = smem_desc_sw128(smem_u32(stage_base), 1024, 16);
+            const uint64_t dB0 = smem_desc_sw128(smem_u32(stage_base) + GEMM_STAGE_A_BYTES, 1024, 16);
             int s = 0;
             uint32_t ph = 0;
             int as = 0;
@@ -179,14 +182,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 for (int it = 0; it < k_iters; ++it) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + GEMM_STAGE_A_BYTES;
+                    const uint64_t da = desc_advance(dA0, s * Cfg::STAGE_BYTES);
+                    const uint64_t db = desc_advance(dB0, s * Cfg::STAGE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        const uint64_t da = smem_desc_sw128(sa + k * 32, 1024, 16);
-                        const uint64_t db = smem_desc_sw128(sb + k * 32, 1024, 16);
-                        umma_f16(d_tmem, da, db, idesc, (it | k) != 0);
-                    }
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (it | k) != 0);
                     umma_commit(&empty[s]);
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int chalf = e >> 2;
         uint8_t* buf = staging + e * GEMM_EPI_BUF_BYTES;          // [32 rows][128 B]; 16-B chunk c of row r at (c ^ (r&7))*16
         uint8_t* my_row = buf + lane * 128;
+        const uint32_t my_row_s = smem_u32(my_row);
         const int sw = lane & 7;
         uint64_t* my_rbar = &rbar[e];
         uint32_t rph = 0;
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                     rph ^= 1;
 #pragma unroll
                                     for (int c4 = 0; c4 < 8; ++c4) {
-                                        const float4 v = *reinterpret_cast<const float4*>(my_row + ((c4 ^ sw) << 4));
+                                        const float4 v = lds128f(my_row_s + ((c4 ^ sw) << 4));
                                         const int b = sp * 32 + 4 * c4;
                                         r[b] = __float_as_uint(__uint_as_float(r[b]) + v.x);
                                         r[b + 1] = __float_as_uint(__uint_as_float(r[b + 1]) + v.y);
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                                 for (int c4 = 0; c4 < 8; ++c4) {
                                     const int b = sp * 32 + 4 * c4;
-                                    *reinterpret_cast<uint4*>(my_row + ((c4 ^ sw) << 4)) = make_uint4(r[b], r[b + 1], r[b + 2], r[b + 3]);
+                                    sts128(my_row_s + ((c4 ^ sw) << 4), r[b], r[b + 1], r[b + 2], r[b + 3]);
                                 }
                                 fence_proxy_async_smem();
                                 __syncwarp();
@@ -329,8 +330,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         __syncwarp();
 #pragma unroll
                         for (int c4 = 0; c4 < 8; ++c4)
-                            *reinterpret_cast<uint4*>(my_row + ((c4 ^ sw) << 4)) =
-                                make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+                            sts128(my_row_s + ((c4 ^ sw) << 4), pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                         for (int c4 = 0; c4 < 8; ++c4) {
                             const int b = sp * 32 + 4 * c4;
-                            *reinterpret_cast<uint4*>(my_row + ((c4 ^ sw) << 4)) = make_uint4(r[b], r[b + 1], r[b + 2], r[b + 3]);
+                            sts128(my_row_s + ((c4 ^ sw) << 4), r[b], r[b + 1], r[b + 2], r[b + 3]);
                         }
                         __syncwarp();
                         const int n = ncol0 + sp * 32 + lane;

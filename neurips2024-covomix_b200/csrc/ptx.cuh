@@ -58,6 +58,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// explicit shared-space vector accesses (a generic pointer would compile to ST.E / LD.E through the generic window)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -153,6 +163,9 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t sbo
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// Advance a descriptor's start address by `bytes` (a multiple of 16; stays inside the 14-bit address field).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (bytes >> 4); }
+
 // Instruction descriptor for kind::f16: [4,6) D fmt (1 = f32), [7,10) A fmt, [10,13) B fmt (0 = f16, 1 = bf16),
 // [15] A major, [16] B major (0 = K-major, 1 = MN-major), [17,23) N >> 3, [24,29) M >> 4.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_fmt, int a_mn_major, int b_mn_major) {
