@@ -319,7 +319,7 @@ def run_b200(args):
             "dtype": "bf16 operands / f32 accumulate (flow), fp16 operands / f32 accumulate (vocoder)", "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B * world, "seq_len": N, "parallelism": f"utterance-sharded x{world}",
                        "cond_scale": 0.7, "l2": "working set (0.8 GB weights + 1.2 GB activations) larger than L2; no flush needed"},
-            "clocks": clocks, "gpu_launches": launches,
+            "clocks": clocks, "gpu_launches": launches * world,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "ode_step_ms": ode_step_ms, "roofline": roofline,
@@ -331,6 +331,60 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def run_vocoder_sweep(args):
+    """BASELINE config C5: HiFi-GAN throughput sweep, mel length x batch; one JSON line per point on rank 0.
+    Traffic model per layer-by-layer execution (what this implementation does): every conv reads its 16-bit input and
+    writes a 16-bit and/or fp32 output (+ fp32 residual read) -- reported as `model_gbs`; FLOPs are algorithmic."""
+    import covomix_b200  # noqa: F401
+    from covomix_b200 import _native as nat, synthetic as syn
+    from covomix_b200.vocoder import B200Generator
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    gen = B200Generator(syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234), syn.HIFIGAN_COVOMIX, dev)
+    pk = peaks()
+    g = torch.Generator().manual_seed(5)
+    out = []
+    for T in (256, 1024, 4096, 16384):
+        for B in (1, 8, 32):
+            if B * T > 32 * 4096:
+                continue
+            mel = syn.synthetic_logmel(g, B, 80, T).to(dev)
+            for _ in range(3):
+                gen(mel)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(3, args.steps)
+            e0.record()
+            for _ in range(reps):
+                gen(mel)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            with nat.profile() as prof:
+                gen(mel)
+            pr = prof.result
+            flops = 281.3e6 * T * B
+            # bytes moved by the layer-by-layer schedule: per output sample-channel of a stage with C padded channels
+            c_pad, t_len, byt = [512, 256, 128, 64, 64], T, 0.0
+            byt += B * T * (80 * 4 + 128 * 2 + 128 * 2 + c_pad[0] * 2)
+            for i, (u, k) in enumerate(zip((5, 4, 4, 2), (8, 8, 4, 4))):
+                t_out = (t_len - 1) * u - 2 * ((k - u) // 2) + k
+                n = B * t_out * c_pad[i + 1]
+                byt += B * t_len * c_pad[i] * 2 + n * 6                      # upsample: read in, write f32 + 16-bit
+                byt += 3 * (3 * (n * 2 + n * 2) + 3 * (n * 2 + n * 4 + n * 4 + n * 2))   # 3 resblocks x 3 x (c1: r+w, c2: r + res + w f32 + w h)
+                byt += 3 * n * 4 + n * 2                                      # stage mean
+                t_len = t_out
+            byt += B * t_len * (64 * 2 * 1 + 4)
+            line = {"metric": "audio-seconds/sec (RTF), HiFi-GAN only", "workload": "C5 vocoder sweep", "T": T, "B": B,
+                    "ms": ms, "value": B * T / FRAME_RATE / (ms * 1e-3), "unit": "audio-s/s",
+                    "achieved_tflops": flops / (ms * 1e-3) / 1e12, "frac_of_tensor_peak": flops / (ms * 1e-3) / 1e12 / pk["tflops"],
+                    "model_gbs": byt / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": byt / (ms * 1e-3) / 1e9 / pk["hbm"],
+                    "kernel_ms": {k: round(v[0], 3) for k, v in pr.items() if v[2]}, "launches": gen.launches_per_forward()}
+            out.append(line)
+            print(json.dumps(line), flush=True)
+    return out
 
 
 def cpu_baseline(wl, cfg):
@@ -368,10 +422,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS) + ["c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "c5":
+        run_vocoder_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

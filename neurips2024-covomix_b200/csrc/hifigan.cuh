@@ -58,6 +58,8 @@ inline int64_t hifi_out_len(const covo_hifigan_cfg& c, int T) {
     return L;
 }
 
+// Buffers of one stage are dead once the next stage's ConvTranspose1d has consumed `out_act`, so all stages share
+// one scratch region (sized for the largest stage) and the stage outputs ping-pong between two regions.
 inline size_t hifi_layout(const covo_hifigan* h, HifiPlan& p) {
     const covo_hifigan_cfg& c = h->cfg;
     Arena a(p.ws, static_cast<size_t>(-1));
@@ -66,6 +68,7 @@ inline size_t hifi_layout(const covo_hifigan* h, HifiPlan& p) {
     p.pre_act = a.take<uint16_t>(B * p.T * pad64(hifi_chan(c, -1)));
     p.stages.assign(c.num_upsamples, HifiStage());
     int t = p.T;
+    size_t max_n = 0;
     for (int i = 0; i < c.num_upsamples; ++i) {
         HifiStage& s = p.stages[i];
         s.stride = c.upsample_rates[i];
@@ -79,6 +82,16 @@ inline size_t hifi_layout(const covo_hifigan* h, HifiPlan& p) {
         s.t_out = (t - 1) * s.stride - 2 * s.pad + s.ksize;
         t = s.t_out;
         const size_t n = B * s.t_out * s.c_out_pad;
+        if (n > max_n) max_n = n;
+    }
+    uint16_t* out_pp[2] = {a.take<uint16_t>(max_n), a.take<uint16_t>(max_n)};
+    a.off = align_up(a.off, 256);
+    const size_t scratch0 = a.off;
+    size_t scratch_end = scratch0;
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        HifiStage& s = p.stages[i];
+        const size_t n = B * s.t_out * s.c_out_pad;
+        a.off = scratch0;
         s.x = a.take<float>(n);
         s.a0 = a.take<uint16_t>(n);
         for (int j = 0; j < c.num_kernels; ++j) {
@@ -86,9 +99,10 @@ inline size_t hifi_layout(const covo_hifigan* h, HifiPlan& p) {
             s.ar[j] = a.take<uint16_t>(n);
             s.hr[j] = a.take<uint16_t>(n);
         }
-        s.out_act = a.take<uint16_t>(n);
+        s.out_act = out_pp[i & 1];
+        if (a.off > scratch_end) scratch_end = a.off;
     }
-    return align_up(a.off, 256);
+    return align_up(scratch_end, 256);
 }
 
 inline ASource a3d(const void* ptr, int C, int T, int B) {

@@ -85,11 +85,25 @@ class B200Generator:
         ws = self._ws.get(key)
         if ws is None:
             nbytes = nat.lib().covo_hifigan_workspace_bytes(self._h, B, T)
-            if len(self._ws) >= 4:
+            while len(self._ws) >= 2:                       # keep at most two call shapes resident
                 self._ws.pop(next(iter(self._ws)))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
+
+    # receptive field of the generator is ~20.4 mel frames per side; chunks of a long input are
+    # computed independently with this halo and stitched (exact away from the sequence ends, see the locality test)
+    HALO = 24
+    MAX_FRAMES_PER_CALL = 16384                             # B*T per library call: bounds the workspace to ~6 GB
+
+    def _forward_one(self, x: torch.Tensor, code: int, tdt) -> torch.Tensor:
+        B, _, T = x.shape
+        wav = torch.empty(B, 1, self.out_len(T), dtype=tdt, device=self.device)
+        ws = self._workspace(B, T)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib().covo_hifigan_forward(self._h, _ptr(x), _ptr(wav), B, T, code, _ptr(ws), ws.numel(),
+                                                 C.c_void_p(stream)), "covo_hifigan_forward")
+        return wav
 
     @torch.inference_mode()
     def forward(self, mel: torch.Tensor, out_dtype: str = "f32") -> torch.Tensor:
@@ -98,14 +112,22 @@ class B200Generator:
             raise ValueError(f"mel must be [{self.h.num_mels}, T] or [B, {self.h.num_mels}, T], got {tuple(mel.shape)}")
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         B, _, T = x.shape
-        L = self.out_len(T)
         code, tdt = {"f32": (nat.COVO_WAV_F32, torch.float32), "f16": (nat.COVO_WAV_F16, torch.float16),
                      "i16": (nat.COVO_WAV_I16, torch.int16)}[out_dtype]
-        wav = torch.empty(B, 1, L, dtype=tdt, device=self.device)
-        ws = self._workspace(B, T)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        nat.check(nat.lib().covo_hifigan_forward(self._h, _ptr(x), _ptr(wav), B, T, code, _ptr(ws), ws.numel(),
-                                                 C.c_void_p(stream)), "covo_hifigan_forward")
+        if B * T <= self.MAX_FRAMES_PER_CALL:
+            return self._forward_one(x, code, tdt)
+        hop, halo = self.h.hop, self.HALO
+        tc = max(4 * halo, self.MAX_FRAMES_PER_CALL // B)            # frames produced per chunk
+        if tc >= T:                                                  # a single item is too long only through B: split batch
+            return torch.cat([self.forward(x[b:b + 1], out_dtype) for b in range(B)], dim=0)
+        wav = torch.empty(B, 1, self.out_len(T), dtype=tdt, device=self.device)
+        for s in range(0, T, tc):
+            e = min(T, s + tc)
+            s0, e0 = max(0, s - halo), min(T, e + halo)
+            part = self._forward_one(x[:, :, s0:e0].contiguous(), code, tdt)
+            lo = (s - s0) * hop
+            hi = part.shape[-1] if e == T else (e - s0) * hop
+            wav[:, :, s * hop:s * hop + (hi - lo)] = part[:, :, lo:hi]
         return wav
 
     __call__ = forward

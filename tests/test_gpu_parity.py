@@ -236,5 +236,14 @@ def test_hifigan_full_size_properties(dev, vocoder):
     crop = gen(mel[3:4, :, :700])
     keep = (700 - 24) * 160
     assert rel_l2(crop[..., :keep], w3[..., :keep]) < 1e-6
-    long = gen(syn.synthetic_logmel(torch.Generator().manual_seed(12), 1, 80, 4096).to(dev))
+    long_mel = syn.synthetic_logmel(torch.Generator().manual_seed(12), 1, 80, 4096).to(dev)
+    long = gen(long_mel)
     assert long.shape == (1, 1, 160 * 4096 + 32) and torch.isfinite(long).all()
+    # time-chunked execution with a receptive-field halo (used for inputs whose workspace would not fit) is exact
+    old = gen.MAX_FRAMES_PER_CALL
+    try:
+        gen.MAX_FRAMES_PER_CALL = 1000
+        chunked = gen(long_mel)
+    finally:
+        gen.MAX_FRAMES_PER_CALL = old
+    assert chunked.shape == long.shape and rel_l2(chunked, long) < 1e-6
