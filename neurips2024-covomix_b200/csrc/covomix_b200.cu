@@ -297,7 +297,9 @@ int covo_dbg_attention(const void* qkv_bf16, void* out_bf16, int Bt, int N, int 
         a.heads = heads;
         a.inner = inner;
         a.scale_log2e = 1.4426950408889634f * 0.125f;
-        dim3 grid(ceil_div(N, ATT_BM), heads, Bt);
+        a.n_qt = ceil_div(N, ATT_BM);
+        a.n_items = a.n_qt * heads * Bt;
+        const int grid = a.n_items < di.num_sms ? a.n_items : di.num_sms;
         attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
     }
     COVO_CK(cudaGetLastError());

@@ -267,6 +267,8 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
         p.attn.heads = c.heads;
         p.attn.inner = inner;
         p.attn.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(c.dim_head));
+        p.attn.n_qt = ceil_div(p.N, ATT_BM);
+        p.attn.n_items = p.attn.n_qt * c.heads * (M / p.N);
     }
     return COVO_OK;
 }
@@ -284,7 +286,7 @@ inline int launch_attention(const covo_flow* h, const FlowPlan& p, cudaStream_t 
             COVO_CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
             attr = true;
         }
-        dim3 grid(ceil_div(p.N, ATT_BM), h->cfg.heads, Bt);
+        const int grid = p.attn.n_items < h->di.num_sms ? p.attn.n_items : h->di.num_sms;
         attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(p.attn);
     }
     COVO_CK(cudaGetLastError());
