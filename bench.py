@@ -100,6 +100,22 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_per_launch():
+    """Mean DRAM read+write bytes per GEMM launch from the committed ncu --set full capture of this workload
+    (profiles/r01_gemm_c3_ncu.md, written by tools/summarize_ncu.py); None if the capture is not there."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_c3_ncu.md")
+    if not os.path.exists(path):
+        return None
+    vals = []
+    for ln in open(path):
+        if ln.startswith("- DRAM traffic"):
+            try:
+                vals.append(float(ln.split("=")[-1].split()[0]) * 1e6)
+            except ValueError:
+                pass
+    return sum(vals) / len(vals) if vals else None
+
+
 def make_inputs(wl, device=None, seed=30):
     from covomix_b200 import synthetic as syn
     cfg = syn.VOMIX if wl["model"] == "vomix" else syn.VOSINGLE
@@ -294,7 +310,9 @@ def run_b200(args):
         roofline = {
             "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM), launches of the velocity net's Linear layers",
             "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tflops"], "peak_source": pk["src"], "traffic": None,
+            "frac": achieved / pk["tflops"], "peak_source": pk["src"],
+            "traffic": ncu_traffic_per_launch() if args.workload == "c3" else None,
+            "traffic_note": "mean dram__bytes_read+write per GEMM launch over the 8 launches of profiles/r01_gemm_c3_ncu.md (bytes)",
             "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "algorithmic_flops_per_launch": g_flops / max(g_n, 1),
             "share_of_step_kernel_time": g_ms / total_kernel_ms if total_kernel_ms else None,
             "how": "one extra instrumented step after the timed region: CUDA events around every launch on the launching stream",
