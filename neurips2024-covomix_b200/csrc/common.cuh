@@ -221,17 +221,26 @@ inline int set_gemm_attr() {
     return COVO_OK;
 }
 
+// Tile width: minimise  waves * cost(BN)  with waves = ceil(tiles / SMs).  cost grows sub-linearly with 1/BN because
+// narrow tiles re-read the A operand from smem more often per FLOP (BN = 64 runs the tensor pipe at ~2/3 rate; measured
+// in profiles/r01_gemm_microbench.txt), so e.g. M = 1300, N = 1024 takes one wave of 88 BN=128 tiles rather than two
+// waves of 176 BN=64 tiles.
 inline int pick_bn(int n_pad, long long m_tiles, int num_sms, int force_bn) {
     if (force_bn) return force_bn;
     const int cands[3] = {256, 128, 64};
+    const double cost[3] = {256.0, 128.0 * 1.10, 64.0 * 1.50};
+    int best = 0;
+    double best_t = 0.0;
     for (int i = 0; i < 3; ++i) {
-        const int bn = cands[i];
-        if (n_pad % bn) continue;
-        if (m_tiles * (n_pad / bn) >= num_sms) return bn;
+        if (n_pad % cands[i]) continue;
+        const long long tiles = m_tiles * (n_pad / cands[i]);
+        const double t = static_cast<double>((tiles + num_sms - 1) / num_sms) * cost[i];
+        if (best == 0 || t < best_t) {
+            best = cands[i];
+            best_t = t;
+        }
     }
-    for (int i = 2; i >= 0; --i)
-        if (n_pad % cands[i] == 0) return cands[i];
-    return 0;
+    return best;
 }
 
 // Fills tensor maps, tile counts and grid.  Epilogue/output-mapping fields of op.args must be set by the caller
