@@ -81,7 +81,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     uint64_t* s_full = bars + 9;    // [2 groups]  MMA -> softmax
     uint64_t* s_free = bars + 11;   //             softmax -> MMA
     uint64_t* p_full = bars + 13;   //             softmax -> MMA
-    uint64_t* p_free = bars + 15;   //             MMA -> softmax
     uint64_t* o_full = bars + 17;   //             MMA -> softmax
     uint64_t* o_free = bars + 19;   //             softmax -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
@@ -104,7 +103,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             mbar_init(&s_full[i], 1);
             mbar_init(&s_free[i], 4);
             mbar_init(&p_full[i], 4);
-            mbar_init(&p_free[i], 1);
             mbar_init(&o_full[i], 1);
             mbar_init(&o_free[i], 4);
         }
@@ -205,8 +203,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                             // A = P from TMEM (16 keys = 8 columns per step); B = V: MN-major, 16 keys = 2048 B apart
                             umma_f16_ts(tmem_O + g * ATT_D, tmem_P + g * 64 + k * 8, desc_advance(bV, k * 2048), idesc_o, k != 0);
                         }
-                        umma_commit(&p_free[g]);
-                        umma_commit(&o_full[g]);
+                        umma_commit(&o_full[g]);                   // also means: P_g has been consumed
                     }
                     umma_commit(&v_empty[st]);
                 }
@@ -280,18 +277,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 for (int i = 0; i < 128; ++i)
                     if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
             }
-            // row max: 4 independent chains of three-input max
-            float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
-                  mx3 = __uint_as_float(s[3]);
+            // row max: 8 independent chains of three-input max (dependency depth 8 instead of 32)
+            float mx[8];
 #pragma unroll
-            for (int i = 4; i + 7 < 128; i += 8) {
-                mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-                mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-                mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+            for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(s[i]);
+#pragma unroll
+            for (int i = 8; i + 15 < 128; i += 16) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) mx[q] = fmax3(mx[q], __uint_as_float(s[i + 2 * q]), __uint_as_float(s[i + 2 * q + 1]));
             }
-            mx0 = fmax3(mx0, __uint_as_float(s[124]), __uint_as_float(s[125]));
-            mx1 = fmax3(mx1, __uint_as_float(s[126]), __uint_as_float(s[127]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mx[q] = fmax3(mx[q], __uint_as_float(s[120 + 2 * q]), __uint_as_float(s[121 + 2 * q]));
+            const float mx0 = fmax3(mx[0], mx[1], mx[2]), mx1 = fmax3(mx[3], mx[4], mx[5]), mx2 = fmaxf(mx[6], mx[7]), mx3 = mx2;
             const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
             TR(3);
             const float alpha = ex2_approx((m_run - m_new) * c);    // first tile: exp2(-inf) = 0
@@ -314,8 +311,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 s[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
             }
             TR(4);
-            // P buffer must have been consumed by the PV MMA of the previous tile
-            mbar_wait(&p_free[g], (it & 1) ^ 1);
+            // P must have been consumed by the PV MMA of the previous tile: that is the same commit that publishes
+            // O(it-1), so wait for it once here and fold the previous tile's O into the accumulator right away
+            if (j > 0) accumulate_O(it - 1, alpha_prev);
             TR(5);
             // P -> TMEM: thread = row, column i = keys (2i, 2i+1) as a bf16 pair
             tmem_st_32x32(tP, &s[0]);
@@ -327,8 +325,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             TR(6);
             l_run = fmaf(l_run, alpha, (l0 + l1) + (l2 + l3));
             m_run = m_new;
-            // deferred accumulation of the previous tile's O (its MMA ran while we did this tile's softmax)
-            if (j > 0) accumulate_O(it - 1, alpha_prev);
             TR(7);
             alpha_prev = alpha;
         }
