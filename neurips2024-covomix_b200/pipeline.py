@@ -1,0 +1,50 @@
+"""Batching / post-processing glue around the two accelerated call sites.
+
+The reference scripts loop one utterance at a time (dialogue_generation.py:283): build ``phone_input`` / ``mel_input`` /
+``mask`` -> ``model.synthesis_sample`` -> ``sampled[:, mask]`` -> ``mel_decode_to_wav`` -> int16
+(monologue_generation.py:160-177).  ``synthesize`` does the same for a LIST of utterances, but groups them into
+equal-length batches (the velocity net has no padding mask, so a batch is exact only for equal-length items) for the
+sampler and into equal-length batches of generated frames for the vocoder, and returns the int16 waveforms in input order.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+
+from .sharding import plan_batches
+
+
+def synthesize(sampler, generator, items: Sequence[Dict[str, torch.Tensor]], cond_scale: float = 0.7, batch: int = 8,
+               vocoder_batch: int = 8) -> List[np.ndarray]:
+    """items[i] = {"phoneme_ids": Long[N] or [N,2], "cond": Float[N,dim_in], "mask": Bool[N][, "y0": Float[N,80]]} (one
+    utterance, as the scripts build them) -> list of int16 arrays (``mel_decode_to_wav`` semantics), same order as ``items``."""
+    device = sampler.device
+    mels: List[torch.Tensor] = [None] * len(items)
+    for n, idx in plan_batches([int(it["cond"].shape[0]) for it in items], batch):
+        ids = torch.stack([items[i]["phoneme_ids"] for i in idx]).to(device)
+        cond = torch.stack([items[i]["cond"] for i in idx]).to(device)
+        mask = torch.stack([items[i]["mask"] for i in idx]).to(device)
+        kw = {}
+        if all("y0" in items[i] for i in idx):                                    # optional: caller-supplied noise (tests)
+            kw["y0"] = torch.stack([items[i]["y0"] for i in idx]).to(device)
+        sampled = sampler.sample(phoneme_ids=ids, cond=cond, mask=mask, cond_scale=cond_scale, **kw)
+        for k, i in enumerate(idx):
+            mels[i] = sampled[k][mask[k]].transpose(0, 1).contiguous()          # [80, T_i]: sampled[:, mask].permute(0,2,1)
+    out: List[np.ndarray] = [None] * len(items)
+    for t, idx in plan_batches([int(m.shape[1]) for m in mels], vocoder_batch):
+        if t == 0:
+            for i in idx:
+                out[i] = np.zeros(0, dtype=np.int16)
+            continue
+        wav = generator(torch.stack([mels[i] for i in idx]), out_dtype="i16")   # fused x32768 + int16 cast
+        wav = wav.reshape(len(idx), -1).cpu().numpy()
+        for k, i in enumerate(idx):
+            out[i] = wav[k]
+    return out
+
+
+def concat_turns(turns: Sequence[np.ndarray]) -> np.ndarray:
+    """dialogue_generation.py:189: per-turn audio of `--mode covosingle` dialogues is concatenated."""
+    return np.concatenate(list(turns)) if len(turns) else np.zeros(0, dtype=np.int16)
