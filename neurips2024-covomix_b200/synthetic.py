@@ -222,3 +222,117 @@ def synthetic_flow_inputs(cfg: FlowConfig, B: int, N: int, prompt: int = 150, se
     mask = torch.zeros(B, N, dtype=torch.bool)
     mask[:, prompt:] = True
     return ids, cond, y0, mask
+
+
+# --------------------------------------------------------------------------------------
+# text-to-semantic (CoSingle / CoMix): SURVEY.md section 8f rank 1
+# --------------------------------------------------------------------------------------
+
+@dataclass(frozen=True)
+class T2SConfig:
+    """Arguments of ``TextToSemantic(...)`` (covomix/covomix_model/text2semantic.py:417-451) as passed by
+    conditional_model.py:122-135 with running_command/T2S_Co{Single,Mix}.sh."""
+    dim: int = 512                       # --CoVoMix_dim_transformer: encoder width == cross-attention context width
+    source_depth: int = 4
+    target_depth: int = 4
+    heads: int = 8
+    dim_head: int = 64
+    num_text_token_ids: int = 30530
+    num_semantic_token_ids: int = 501    # --text2semantic_tokens
+    two_output: bool = False             # --text2semantic_two_output (CoMix)
+    target_transformer_dim: int = 512    # --target_transformer_dim (1024 for CoMix)
+    ff_mult: int = 4
+    text_pad_id: int = 0
+    semantic_pad_id: int = -1
+
+    @property
+    def inner(self) -> int:              # heads * dim_head (text2semantic.py:190-191)
+        return self.heads * self.dim_head
+
+    def ff_inner(self, dim: int) -> int:  # text2semantic.py:161
+        return int(dim * self.ff_mult * 2 / 3)
+
+    @property
+    def n_out(self) -> int:
+        return 2 if self.two_output else 1
+
+    @property
+    def dim_emb(self) -> int:            # width of one semantic embedding row (text2semantic.py:512-515)
+        return self.target_transformer_dim // self.n_out
+
+    @property
+    def text_eos_id(self) -> int:        # text2semantic.py:491-494
+        return self.num_text_token_ids
+
+    @property
+    def semantic_eos_id(self) -> int:
+        return self.num_semantic_token_ids
+
+    @property
+    def n_logits(self) -> int:           # tied to the embedding table, which has the EOS row (text2semantic.py:541)
+        return self.num_semantic_token_ids + 1
+
+
+COSINGLE = T2SConfig()
+COMIX = T2SConfig(two_output=True, target_transformer_dim=1024)
+
+
+def synthetic_t2s_state_dict(cfg: T2SConfig, seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """State dict of ``TextToSemantic`` (keys as in its ``state_dict()``; the three tied copies of the semantic
+    embedding and the two of the text embedding are the same tensor).  Norm gains are perturbed away from 1."""
+    g = torch.Generator().manual_seed(seed)
+    d, dt, inner = cfg.dim, cfg.target_transformer_dim, cfg.inner
+    sd: Dict[str, torch.Tensor] = {}
+    # std 0.1: logits = emb . h have std ~ 0.1 * sqrt(dim_emb) ~ 2, so that top-k + Gumbel sampling actually depends
+    # on the noise (with N(0,1) rows the tied logits have std ~ 22 and decoding is greedy whatever the seed)
+    sem = _randn(g, cfg.n_logits, cfg.dim_emb, std=0.1)
+    txt = _randn(g, cfg.num_text_token_ids + 1, d)
+    sd["semantic_token_emb.weight"] = sem
+    sd["token_emb.speech.weight"] = sem
+    sd["token_emb.text.weight"] = txt
+    sd["start_token.speech"] = _randn(g, dt)
+    sd["start_token.text"] = _randn(g, d)
+    sd["to_logits.speech.weight"] = sem
+    sd["to_logits.text.weight"] = txt
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, cfg.dim_head, 2).float() / cfg.dim_head))
+
+    def attn(p: str, dim: int, dim_ctx: int, cross: bool):
+        if not cross:
+            sd[p + "rotary_emb.freqs"] = inv_freq.clone()
+        else:
+            sd[p + "null_kv"] = _randn(g, 2, cfg.heads, 1, cfg.dim_head)
+        sd[p + "norm.gamma"] = 1.0 + _randn(g, dim, std=0.1)
+        sd[p + "to_q.0.weight"] = _randn(g, inner, dim, std=dim ** -0.5)
+        sd[p + "to_kv.0.weight"] = _randn(g, 2 * inner, dim_ctx, std=dim_ctx ** -0.5)
+        sd[p + "to_out.weight"] = _randn(g, dim, inner, std=inner ** -0.5)
+
+    def ff(p: str, dim: int):
+        fi = cfg.ff_inner(dim)
+        sd[p + "0.gamma"] = 1.0 + _randn(g, dim, std=0.1)
+        sd[p + "1.weight"] = _randn(g, 2 * fi, dim, std=dim ** -0.5)
+        sd[p + "1.bias"] = _randn(g, 2 * fi, std=0.02)
+        sd[p + "4.weight"] = _randn(g, dim, fi, std=fi ** -0.5)
+        sd[p + "4.bias"] = _randn(g, dim, std=0.02)
+
+    for L in range(cfg.source_depth):
+        attn(f"source_transformer.layers.{L}.0.", d, d, False)
+        ff(f"source_transformer.layers.{L}.2.", d)
+    sd["source_transformer.final_norm.gamma"] = 1.0 + _randn(g, d, std=0.1)
+    for L in range(cfg.target_depth):
+        attn(f"target_transformer.layers.{L}.0.", dt, dt, False)
+        attn(f"target_transformer.layers.{L}.1.", dt, d, True)
+        ff(f"target_transformer.layers.{L}.2.", dt)
+    sd["target_transformer.final_norm.gamma"] = 1.0 + _randn(g, dt, std=0.1)
+    return sd
+
+
+def synthetic_text_ids(cfg: T2SConfig, B: int, S: int, seed: int = 30, ragged: bool = True) -> torch.Tensor:
+    """BERT-tokenizer-like ids in [1, num_text_token_ids), right-padded with ``text_pad_id`` when ragged
+    (``tokenizer([txt], padding=True)``, dialogue_generation.py:335)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1, cfg.num_text_token_ids, (B, S), generator=g, dtype=torch.int64)
+    if ragged:
+        for b in range(1, B):
+            keep = max(1, S - (b * 3) % max(S // 2, 1))
+            ids[b, keep:] = cfg.text_pad_id
+    return ids
