@@ -117,6 +117,52 @@ int covo_hifigan_forward(covo_hifigan* h, const float* mel, void* wav, int B, in
                          size_t workspace_bytes, void* stream);
 int covo_hifigan_launches_per_forward(const covo_hifigan* h);
 
+/* ---- text-to-semantic (CoSingle / CoMix) -----------------------------------------------------------------
+ * Mirrors the arguments of TextToSemantic(...) (covomix/covomix_model/text2semantic.py:417-451) as passed by
+ * CoVoMixModel.__init__ (covomix/conditional_model.py:122-135; running_command/T2S_Co{Single,Mix}.sh). */
+enum { COVO_T2S_W_BF16 = 0, COVO_T2S_W_F32 = 1 };   /* storage type of the decoder's matrices (accumulation is fp32) */
+typedef struct covo_t2s_cfg {
+    int32_t dim;                     /* 512: source transformer / cross-attention context width */
+    int32_t source_depth;            /* 4 */
+    int32_t target_depth;            /* 4 (<= 8) */
+    int32_t heads;                   /* 8 */
+    int32_t dim_head;                /* 64 (only value supported) */
+    int32_t num_text_token_ids;      /* 30530; id 30530 is the text EOS (text2semantic.py:491-494) */
+    int32_t num_semantic_token_ids;  /* 501;   id 501 is the semantic EOS */
+    int32_t two_output;              /* 0 CoSingle, 1 CoMix (two token streams per step, :768-776) */
+    int32_t target_transformer_dim;  /* 512 CoSingle, 1024 CoMix */
+    int32_t ff_mult;                 /* 4 */
+    int32_t text_pad_id;             /* 0 */
+    int32_t weight_format;           /* COVO_T2S_W_* */
+} covo_t2s_cfg;
+
+typedef struct covo_t2s covo_t2s;
+
+/* packed_weights: HOST pointer to a blob produced by covomix_b200.packing.pack_t2s_weights. */
+int covo_t2s_create(const covo_t2s_cfg* cfg, const void* packed_weights, size_t bytes, int device, covo_t2s** out);
+int covo_t2s_destroy(covo_t2s* h);
+size_t covo_t2s_workspace_bytes(const covo_t2s* h, int B, int S, int max_length);
+
+/* Replaces TextToSemantic.generate(source, source_type='text', target_type='speech', ...) (text2semantic.py:659-848; the
+ * non-beam, non-speculative branch; cond_scale == 1) == TextToSemanticWrapper.sample (:1237-1251):
+ *   text_ids   int64 [B,S]   text token ids AFTER set_eos_id (:57-66, done by the host mirror), pad = text_pad_id
+ *   u          f32   [max_length, n_out, B, n_logits]  uniform(0,1) draws of gumbel_noise (:108-113) in the reference's
+ *              draw order (the caller draws them with torch, as for y0 of the flow sampler); n_logits = 502
+ *   forced     int64 [B, n_out, max_length] or NULL: teacher forcing -- token fed back at each position (parity tests)
+ *   tokens     int64 [B, n_out, max_length]  sampled ids (positions >= steps are not written)
+ *   result     int32 [4] (device): [0] decoding steps executed, [1] 1 if the EOS rule ended the loop (:804-826),
+ *              [2] 1 if the kernel aborted on a stuck grid barrier
+ *   logits_out f32 [max_length, n_out, B, n_logits] or NULL: pre-filter logits of every step
+ *   enc_out    f32 [B, S, dim] or NULL: output of the source transformer (parity tests)
+ *   top_k: ceil(0.1 * n_logits) = 51 for filter_logits_fn = top_k (:126-132). */
+int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, const int64_t* forced, int64_t* tokens,
+                      int32_t* result, float* logits_out, float* enc_out, int B, int S, int max_length, float temperature,
+                      int top_k, void* workspace, size_t workspace_bytes, void* stream);
+/* Kernels launched by one covo_t2s_generate call (the whole autoregressive loop is one of them). */
+int covo_t2s_launches_per_generate(const covo_t2s* h);
+/* Bytes of decoder matrices one decoding step streams (the quantity the step is bound by). */
+size_t covo_t2s_weight_bytes_per_step(const covo_t2s* h);
+
 /* ---- misc ------------------------------------------------------------------------------------------ */
 const char* covo_last_error(void);
 int covo_version(void);

@@ -21,6 +21,8 @@ EXPORTS = (
     "covo_flow_launches_per_sample", "covo_hifigan_create", "covo_hifigan_destroy", "covo_hifigan_workspace_bytes",
     "covo_hifigan_out_len", "covo_hifigan_forward", "covo_hifigan_launches_per_forward", "covo_last_error",
     "covo_version", "covo_dbg_gemm", "covo_dbg_attention", "covo_prof_begin", "covo_prof_end",
+    "covo_t2s_create", "covo_t2s_destroy", "covo_t2s_workspace_bytes", "covo_t2s_generate",
+    "covo_t2s_launches_per_generate", "covo_t2s_weight_bytes_per_step",
 )
 
 
@@ -38,6 +40,14 @@ class HifiganCfg(C.Structure):
         ("resblock_dilations", (C.c_int32 * 4) * 4), ("resblock_type", C.c_int32), ("h_format", C.c_int32),
     ]
 
+
+class T2SCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "dim", "source_depth", "target_depth", "heads", "dim_head", "num_text_token_ids", "num_semantic_token_ids",
+        "two_output", "target_transformer_dim", "ff_mult", "text_pad_id", "weight_format")]
+
+
+COVO_T2S_W_BF16, COVO_T2S_W_F32 = 0, 1
 
 _lib = None
 
@@ -71,6 +81,14 @@ def lib() -> C.CDLL:
     L.covo_hifigan_launches_per_forward.argtypes = [vp]
     L.covo_dbg_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.covo_dbg_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.covo_t2s_create.argtypes = [C.POINTER(T2SCfg), vp, sz, i32, C.POINTER(vp)]
+    L.covo_t2s_destroy.argtypes = [vp]
+    L.covo_t2s_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    L.covo_t2s_workspace_bytes.restype = sz
+    L.covo_t2s_generate.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, sz, vp]
+    L.covo_t2s_launches_per_generate.argtypes = [vp]
+    L.covo_t2s_weight_bytes_per_step.argtypes = [vp]
+    L.covo_t2s_weight_bytes_per_step.restype = sz
     L.covo_prof_begin.argtypes = []
     L.covo_prof_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), i32]
     for name in EXPORTS:
@@ -81,7 +99,8 @@ def lib() -> C.CDLL:
     return L
 
 
-PROF_CLASSES = ("gemm_tc", "attention_tc", "rmsnorm", "convpos", "elementwise", "prologue", "gemm_tc_vocoder")
+PROF_CLASSES = ("gemm_tc", "attention_tc", "rmsnorm", "convpos", "elementwise", "prologue", "gemm_tc_vocoder",
+                "t2s_decode")
 
 
 class profile:

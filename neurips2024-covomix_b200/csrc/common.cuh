@@ -152,7 +152,7 @@ inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
 // ------------------------------------------------------------------------------------------------ launch profiler
 // Opt-in (covo_prof_begin/_end): brackets every kernel launch with CUDA events on the launching stream so that
 // bench.py can report per-kernel-class time shares and the dominant kernel's achieved FLOP/s.  Off in normal use.
-enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_NORM = 2, PC_CONVPOS = 3, PC_ELEMWISE = 4, PC_PROLOGUE = 5, PC_GEMM_VOC = 6, PC_COUNT = 7 };
+enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_NORM = 2, PC_CONVPOS = 3, PC_ELEMWISE = 4, PC_PROLOGUE = 5, PC_GEMM_VOC = 6, PC_T2S_DECODE = 7, PC_COUNT = 8 };
 struct ProfRec {
     int cat;
     double flops;

@@ -1,6 +1,7 @@
 // libcovomix_b200.so -- C ABI (include/covomix_b200.h) over the sm_100a kernels.
 #include "flow.cuh"
 #include "hifigan.cuh"
+#include "t2s.cuh"
 
 using namespace covo;
 
@@ -214,6 +215,160 @@ int covo_hifigan_forward(covo_hifigan* h, const float* mel, void* wav, int B, in
     HifiPlan* p = nullptr;
     COVO_TRY(hifi_get_plan(h, B, T, workspace, workspace_bytes, &p));
     return hifi_enqueue(h, *p, mel, wav, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+// ====================================================================================== text-to-semantic
+int covo_t2s_create(const covo_t2s_cfg* cfg, const void* packed_weights, size_t bytes, int device, covo_t2s** out) {
+    if (!cfg || !packed_weights || !out) return fail(COVO_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->dim_head != T2S_DH) return fail(COVO_ERR_INVALID, "dim_head=%d unsupported (64 only)", cfg->dim_head);
+    if (cfg->target_depth < 1 || cfg->target_depth > T2S_MAX_DEPTH || cfg->source_depth < 0)
+        return fail(COVO_ERR_INVALID, "target_depth=%d / source_depth=%d out of range", cfg->target_depth, cfg->source_depth);
+    if (cfg->dim % 8 || cfg->target_transformer_dim % 16 || cfg->heads < 1 || (cfg->num_semantic_token_ids + 1) % 2)
+        return fail(COVO_ERR_INVALID, "unsupported dims (dim=%d, target dim=%d, heads=%d, semantic ids=%d)", cfg->dim,
+                    cfg->target_transformer_dim, cfg->heads, cfg->num_semantic_token_ids);
+    if (cfg->weight_format != COVO_T2S_W_BF16 && cfg->weight_format != COVO_T2S_W_F32)
+        return fail(COVO_ERR_INVALID, "weight_format=%d", cfg->weight_format);
+    DeviceGuard g(device);
+    covo_t2s* h = new covo_t2s();
+    h->cfg = *cfg;
+    int rc = check_device(device, &h->di);
+    if (rc == COVO_OK) rc = h->w.load(packed_weights, bytes);
+    if (rc == COVO_OK) rc = t2s_bind_weights(h);
+    if (rc == COVO_OK) {
+        int coop = 0;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop)
+            rc = fail(COVO_ERR_CUDA, "device %d does not support cooperative launches", device);
+    }
+    if (rc != COVO_OK) {
+        h->w.release();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return COVO_OK;
+}
+
+int covo_t2s_destroy(covo_t2s* h) {
+    if (!h) return COVO_OK;
+    DeviceGuard g(h->di.device);
+    cudaDeviceSynchronize();
+    h->w.release();
+    delete h;
+    return COVO_OK;
+}
+
+size_t covo_t2s_workspace_bytes(const covo_t2s* h, int B, int S, int max_length) {
+    if (!h || B < 1 || B > 8 || S < 1 || max_length < 1) return 0;
+    return t2s_layout(h, t2s_pad_batch(B), S, max_length, nullptr, nullptr);
+}
+
+int covo_t2s_launches_per_generate(const covo_t2s* h) { return h ? t2s_source_launches(h) + 1 : 0; }
+
+size_t covo_t2s_weight_bytes_per_step(const covo_t2s* h) {
+    if (!h) return 0;
+    const size_t Dt = h->cfg.target_transformer_dim, inner = h->inner;
+    const size_t per_layer = 3 * inner * Dt + Dt * inner + inner * Dt + Dt * inner + 2 * static_cast<size_t>(h->ffi) * Dt +
+                             Dt * static_cast<size_t>(h->ffi);
+    const size_t esz = h->wdt == DT_F32 ? 4 : 2;
+    return per_layer * h->cfg.target_depth * esz + static_cast<size_t>(h->n_logits) * h->demb * 4;
+}
+
+int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, const int64_t* forced, int64_t* tokens,
+                      int32_t* result, float* logits_out, float* enc_out, int B, int S, int max_length, float temperature,
+                      int top_k, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !text_ids || !u || !tokens || !result || !workspace) return fail(COVO_ERR_INVALID, "null argument");
+    if (B != 1 && B != 2 && B != 4 && B != 8)
+        return fail(COVO_ERR_INVALID, "B=%d: the decode kernel takes 1, 2, 4 or 8 rows (the host mirror pads)", B);
+    if (S < 1 || max_length < 1 || max_length > 8192) return fail(COVO_ERR_INVALID, "S=%d / max_length=%d out of range", S, max_length);
+    if (top_k < 1 || top_k > h->n_logits) return fail(COVO_ERR_INVALID, "top_k=%d", top_k);
+    DeviceGuard g(h->di.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const covo_t2s_cfg& c = h->cfg;
+    T2SBuffers t;
+    const size_t need = t2s_layout(h, B, S, max_length, workspace, &t);
+    if (need > workspace_bytes) return fail(COVO_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, need);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(COVO_ERR_INVALID, "workspace must be 256-byte aligned");
+    COVO_CK(cudaMemcpyAsync(t.ids, text_ids, static_cast<size_t>(B) * S * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    COVO_CK(cudaMemsetAsync(static_cast<uint8_t*>(workspace) + t.zero_from, 0, t.zero_bytes, st));
+    COVO_TRY(t2s_enqueue_source(h, t, B, S, max_length, st));
+    if (enc_out)
+        COVO_CK(cudaMemcpyAsync(enc_out, t.he, static_cast<size_t>(B) * S * c.dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+    T2SDecArgs a;
+    memset(&a, 0, sizeof(a));
+    const int H = c.heads, n_ctx = S + 1;
+    const size_t ctx_per = static_cast<size_t>(B) * H * n_ctx * T2S_DH, cache_per = static_cast<size_t>(B) * H * max_length * T2S_DH;
+    for (int L = 0; L < c.target_depth; ++L) {
+        const T2SDecLayerW& d = h->dec[L];
+        T2SLayerW& w = a.L[L];
+        w.sa_gamma = d.sa_gamma.as<float>();
+        w.sa_qkv = d.sa_qkv.ptr;
+        w.sa_out = d.sa_out.ptr;
+        w.ca_gamma = d.ca_gamma.as<float>();
+        w.ca_q = d.ca_q.ptr;
+        w.ca_out = d.ca_out.ptr;
+        w.ff_gamma = d.ff_gamma.as<float>();
+        w.ff1 = d.ff1_w.ptr;
+        w.ff1_b = d.ff1_b.as<float>();
+        w.ff2 = d.ff2_w.ptr;
+        w.ff2_b = d.ff2_b.as<float>();
+        w.ctx_k = t.ctx_k + L * ctx_per;
+        w.ctx_v = t.ctx_v + L * ctx_per;
+        w.kcache = t.kcache + L * cache_per;
+        w.vcache = t.vcache + L * cache_per;
+    }
+    a.depth = c.target_depth;
+    a.B = B;
+    a.Dt = c.target_transformer_dim;
+    a.inner = h->inner;
+    a.H = H;
+    a.ffi = h->ffi;
+    a.ffi_pad = h->ffi_pad;
+    a.n_out = h->n_out;
+    a.demb = h->demb;
+    a.n_logits = h->n_logits;
+    a.n_ctx = n_ctx;
+    a.max_len = max_length;
+    a.topk = top_k;
+    a.nsplit_self = a.nsplit_ctx = t2s_nsplit(h->di.num_sms, B, H);
+    a.temperature = temperature;
+    a.eos_id = c.num_semantic_token_ids;
+    a.emb = h->dec_emb.as<float>();
+    a.start = h->dec_start.as<float>();
+    a.final_gamma = h->dec_final.as<float>();
+    a.rope = t.rope;
+    a.ctx_mask = t.cmask;
+    a.x = t.x;
+    a.q = t.q;
+    a.part = t.part;
+    a.hbuf = t.hbuf;
+    a.logits = t.logits;
+    a.u = u;
+    a.forced = reinterpret_cast<const long long*>(forced);
+    a.tokens = reinterpret_cast<long long*>(tokens);
+    a.logits_out = logits_out;
+    a.result = t.result;
+    a.eos_flags = t.eos_flags;
+    a.barrier = t.barrier;
+    const size_t smem = t2s_decode_smem(h, B, n_ctx, max_length);
+    {
+        ProfScope ps(PC_T2S_DECODE, 0.0, st);
+        int rc = COVO_OK;
+#define COVO_T2S_LAUNCH(WT_)                                                     \
+    do {                                                                         \
+        if (B == 1) rc = t2s_launch_decode<WT_, 1>(h, a, smem, st);              \
+        else if (B == 2) rc = t2s_launch_decode<WT_, 2>(h, a, smem, st);         \
+        else if (B == 4) rc = t2s_launch_decode<WT_, 4>(h, a, smem, st);         \
+        else rc = t2s_launch_decode<WT_, 8>(h, a, smem, st);                     \
+    } while (0)
+        if (h->wdt == DT_F32) COVO_T2S_LAUNCH(float);
+        else COVO_T2S_LAUNCH(__nv_bfloat16);
+#undef COVO_T2S_LAUNCH
+        COVO_TRY(rc);
+    }
+    COVO_CK(cudaMemcpyAsync(result, t.result, 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return COVO_OK;
 }
 
 // ====================================================================================== profiler

@@ -18,7 +18,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 import torch
 
-from .synthetic import FlowConfig, HifiganConfig
+from .synthetic import FlowConfig, HifiganConfig, T2SConfig
 
 DT_F32, DT_BF16, DT_F16, DT_I64 = 0, 1, 2, 3
 _ENTRY = struct.Struct("<48sII4QQQ")
@@ -219,4 +219,74 @@ def pack_hifigan_weights(sd: Dict[str, torch.Tensor], cfg: HifiganConfig, h_form
     pp[:, :ch] = wpost[0].t()
     b.add("conv_post.w", pp, DT_F32)
     b.add("conv_post.b", sd["conv_post.bias"].reshape(1), DT_F32)
+    return b.build()
+
+
+# --------------------------------------------------------------------------------------
+# text-to-semantic (CoSingle / CoMix)
+# --------------------------------------------------------------------------------------
+
+def strip_t2s_prefix(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Accept Lightning (``cfm_wrapper.model.*``, conditional_model.py:136), wrapper (``model.*``) or bare keys."""
+    for prefix in ("cfm_wrapper.model.", "model."):
+        if any(k.startswith(prefix) for k in sd):
+            return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    return dict(sd)
+
+
+def t2s_config_from_state_dict(sd: Dict[str, torch.Tensor], heads: int = 8, dim_head: int = 64) -> T2SConfig:
+    """Recover the ``TextToSemantic(...)`` arguments (conditional_model.py:122-135) from tensor shapes."""
+    sd = strip_t2s_prefix(sd)
+    n_text, dim = sd["token_emb.text.weight"].shape
+    n_sem, demb = sd["token_emb.speech.weight"].shape
+    dt = sd["start_token.speech"].shape[0]
+    depth = lambda side: 1 + max(int(k.split(".")[2]) for k in sd if k.startswith(side + "_transformer.layers."))
+    return T2SConfig(dim=dim, source_depth=depth("source"), target_depth=depth("target"), heads=heads, dim_head=dim_head,
+                     num_text_token_ids=n_text - 1, num_semantic_token_ids=n_sem - 1, two_output=dt == 2 * demb,
+                     target_transformer_dim=dt)
+
+
+def pack_t2s_weights(sd: Dict[str, torch.Tensor], cfg: T2SConfig, weight_format: str = "bf16") -> np.ndarray:
+    """Source side in fp32 (runs once per call); the decoder matrices the persistent decode kernel streams every step in
+    bf16 (default) or fp32; norms, biases, the tied semantic embedding / logit table and the cross-attention k/v
+    projection (applied once per call) in fp32."""
+    sd = {k: v.detach().float().cpu() for k, v in strip_t2s_prefix(sd).items()}
+    wdt = DT_F32 if weight_format == "fp32" else DT_BF16
+    b = BlobBuilder()
+    b.add("enc.emb", sd["token_emb.text.weight"], DT_F32)
+    b.add("rope.inv_freq", sd["target_transformer.layers.0.0.rotary_emb.freqs"], DT_F32)
+    for L in range(cfg.source_depth):
+        p, q = f"source_transformer.layers.{L}.", f"enc.L{L}."
+        b.add(q + "attn.gamma", sd[p + "0.norm.gamma"], DT_F32)
+        b.add(q + "q.w", sd[p + "0.to_q.0.weight"], DT_F32)
+        b.add(q + "kv.w", sd[p + "0.to_kv.0.weight"], DT_F32)
+        b.add(q + "out.w", sd[p + "0.to_out.weight"], DT_F32)
+        b.add(q + "ff.gamma", sd[p + "2.0.gamma"], DT_F32)
+        b.add(q + "ff1.w", sd[p + "2.1.weight"], DT_F32)
+        b.add(q + "ff1.b", sd[p + "2.1.bias"], DT_F32)
+        b.add(q + "ff2.w", sd[p + "2.4.weight"], DT_F32)
+        b.add(q + "ff2.b", sd[p + "2.4.bias"], DT_F32)
+    b.add("enc.final.gamma", sd["source_transformer.final_norm.gamma"] if cfg.source_depth else torch.ones(cfg.dim), DT_F32)
+    b.add("dec.emb", sd["token_emb.speech.weight"], DT_F32)
+    b.add("dec.start", sd["start_token.speech"], DT_F32)
+    b.add("dec.final.gamma", sd["target_transformer.final_norm.gamma"], DT_F32)
+    fi = cfg.ff_inner(cfg.target_transformer_dim)
+    fip = _round_up(fi, 8)
+    for L in range(cfg.target_depth):
+        p, q = f"target_transformer.layers.{L}.", f"dec.L{L}."
+        b.add(q + "sa.gamma", sd[p + "0.norm.gamma"], DT_F32)
+        b.add(q + "sa.qkv.w", torch.cat((sd[p + "0.to_q.0.weight"], sd[p + "0.to_kv.0.weight"]), 0), wdt)   # q | k | v rows
+        b.add(q + "sa.out.w", sd[p + "0.to_out.weight"], wdt)
+        b.add(q + "ca.gamma", sd[p + "1.norm.gamma"], DT_F32)
+        b.add(q + "ca.q.w", sd[p + "1.to_q.0.weight"], wdt)
+        b.add(q + "ca.kv.w", sd[p + "1.to_kv.0.weight"], DT_F32)
+        b.add(q + "ca.null_kv", sd[p + "1.null_kv"].reshape(2, cfg.heads, cfg.dim_head), DT_F32)
+        b.add(q + "ca.out.w", sd[p + "1.to_out.weight"], wdt)
+        b.add(q + "ff.gamma", sd[p + "2.0.gamma"], DT_F32)
+        b.add(q + "ff1.w", sd[p + "2.1.weight"], wdt)
+        b.add(q + "ff1.b", sd[p + "2.1.bias"], DT_F32)
+        w2 = torch.zeros(cfg.target_transformer_dim, fip)
+        w2[:, :fi] = sd[p + "2.4.weight"]
+        b.add(q + "ff2.w", w2, wdt)
+        b.add(q + "ff2.b", sd[p + "2.4.bias"], DT_F32)
     return b.build()

@@ -1,0 +1,157 @@
+"""GPU parity tests of the text-to-semantic path (covo_t2s_generate through the C ABI) against the golden vectors
+produced by the real reference ``TextToSemantic.generate`` and against the CPU oracle.
+
+Tolerances (reference arithmetic is fp32):
+  source transformer output (fp32 kernels)                 rel-L2 <= 1e-4
+  logits, fp32 decoder matrices                            rel-L2 <= 1e-4 and sampled tokens IDENTICAL to the reference's
+  logits, bf16 decoder matrices (default), teacher forced  rel-L2 <= 1e-2, >= 90 % of the sampled tokens identical
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import covomix_b200  # noqa: F401
+from covomix_b200 import synthetic as syn
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+CASES = [("comix_b2", "comix"), ("comix_eos", "comix"), ("cosingle_b1", "cosingle")]
+CFGS = {"comix": syn.COMIX, "cosingle": syn.COSINGLE}
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def models(dev):
+    from covomix_b200.t2s import B200TextToSemantic
+    out = {}
+    for name, cfg in CFGS.items():
+        sd = syn.synthetic_t2s_state_dict(cfg, 1234)
+        out[name] = (sd, {fmt: B200TextToSemantic(sd, cfg, dev, weight_format=fmt) for fmt in ("fp32", "bf16")})
+    return out
+
+
+def load_case(case, cfg):
+    g = np.load(os.path.join(GOLDEN, f"t2s_{case}.npz"))
+    ids = syn.synthetic_text_ids(cfg, int(g["B"]), int(g["S"]), seed=int(g["input_seed"]), ragged=bool(g["ragged"]))
+    return g, ids
+
+
+@pytest.mark.parametrize("case,model", CASES)
+def test_fp32_free_running_matches_reference(dev, models, case, model):
+    cfg = CFGS[model]
+    g, ids = load_case(case, cfg)
+    m = models[model][1]["fp32"]
+    L = int(g["max_length"])
+    u = torch.zeros(L, cfg.n_out, int(g["B"]), cfg.n_logits)
+    u[:int(g["steps"])] = torch.from_numpy(g["u"])
+    u[int(g["steps"]):] = 0.5
+    target, mask, dbg = m.generate(ids, max_length=L, noise=u, return_target_mask=True, return_debug=True)
+    assert rel_l2(dbg["enc"], g["enc"]) < 1e-4
+    assert dbg["steps"] == int(g["steps"])
+    assert rel_l2(dbg["logits"], g["logits"]) < 1e-4
+    assert torch.equal(target.cpu(), torch.from_numpy(g["target"]))
+    assert torch.equal(mask.cpu(), torch.from_numpy(g["mask"]))
+
+
+@pytest.mark.parametrize("case,model", CASES)
+def test_bf16_teacher_forced_matches_reference(dev, models, case, model):
+    cfg = CFGS[model]
+    g, ids = load_case(case, cfg)
+    m = models[model][1]["bf16"]
+    steps, B = int(g["steps"]), int(g["B"])
+    ref_tokens = torch.from_numpy(g["target"]).view(B, cfg.n_out, steps).clamp(min=0)
+    _, dbg = m.generate(ids, max_length=steps, noise=torch.from_numpy(g["u"]), forced=ref_tokens, return_debug=True)
+    err = rel_l2(dbg["logits"], g["logits"])
+    agree = float((dbg["tokens"].cpu() == ref_tokens).float().mean())
+    print(f"{case}: bf16 logits rel-L2 {err:.2e}, token agreement {agree:.3f}")
+    assert err < 1e-2
+    assert agree >= 0.9
+
+
+def test_sample_returns_unmasked_tokens_with_eos(dev, models):
+    from oracle import t2s_oracle as orc
+    cfg = syn.COMIX
+    g, ids = load_case("comix_eos", cfg)
+    sd, ms = models["comix"]
+    u = torch.cat((torch.from_numpy(g["u"]), torch.full((8, 2, 1, cfg.n_logits), 0.5)))
+    out = ms["fp32"].sample(ids, noise=u, max_length=u.shape[0])
+    ref = orc.sample(sd, cfg, ids, u, max_length=u.shape[0])
+    assert torch.equal(out.cpu(), ref)
+    assert int((out == cfg.semantic_eos_id).sum()) == 1
+
+
+def test_long_decode_against_oracle(dev, models):
+    """Cache growth over a few hundred positions: teacher-forced logits of the last steps vs the oracle run here."""
+    from oracle import t2s_oracle as orc
+    cfg = syn.COMIX
+    sd, ms = models["comix"]
+    ids = syn.synthetic_text_ids(cfg, 1, 40, seed=5, ragged=False)
+    steps = 200
+    g = torch.Generator().manual_seed(11)
+    u = torch.rand(steps, 2, 1, cfg.n_logits, generator=g)
+    forced = torch.randint(0, 501, (1, 2, steps), generator=g)
+    _, _, _, ref_logits = orc.generate(sd, cfg, ids, u, max_length=steps, forced=forced, return_logits=True)
+    n = ref_logits.shape[0]                         # the oracle may stop early on a sampled EOS
+    for fmt, tol in (("fp32", 1e-4), ("bf16", 1e-2)):
+        _, dbg = ms[fmt].generate(ids, max_length=steps, noise=u, forced=forced, return_debug=True)
+        assert dbg["steps"] == n
+        assert rel_l2(dbg["logits"][n - 20:n], ref_logits[n - 20:n]) < tol
+
+
+def test_batch_rows_are_independent_and_padded(dev, models):
+    """B = 3 (padded to 4 rows inside) with ragged text: every row equals its own B = 1 run (teacher forced)."""
+    cfg = syn.COMIX
+    m = models["comix"][1]["bf16"]
+    ids = syn.synthetic_text_ids(cfg, 3, 17, seed=9, ragged=True)
+    steps = 24
+    g = torch.Generator().manual_seed(3)
+    u = torch.rand(steps, 2, 3, cfg.n_logits, generator=g)
+    forced = torch.randint(0, 501, (3, 2, steps), generator=g)
+    _, dbg = m.generate(ids, max_length=steps, noise=u, forced=forced, return_debug=True)
+    for b in range(3):
+        row = ids[b:b + 1]
+        keep = int((row != cfg.text_pad_id).sum())
+        _, d1 = m.generate(row[:, :keep], max_length=steps, noise=u[:, :, b:b + 1], forced=forced[b:b + 1],
+                           return_debug=True)
+        n = min(d1["steps"], dbg["steps"])
+        assert rel_l2(dbg["logits"][:n, :, b], d1["logits"][:n, :, 0]) < 1e-4
+
+
+def test_full_size_decode_properties(dev, models):
+    """BASELINE shape (30 s dialogue = 1500 positions, B = 8): deterministic, finite, in range, and the loop runs to
+    max_length when EOS is never sampled for every row."""
+    cfg = syn.COMIX
+    m = models["comix"][1]["bf16"]
+    ids = syn.synthetic_text_ids(cfg, 8, 200, seed=4, ragged=True)
+    u = torch.rand(1500, 2, 8, cfg.n_logits, generator=torch.Generator().manual_seed(8))
+    t1, mask1, dbg = m.generate(ids, max_length=1500, noise=u, return_target_mask=True, return_debug=True)
+    t2, _ = m.generate(ids, max_length=1500, noise=u, return_target_mask=True)
+    assert torch.equal(t1, t2)
+    steps = dbg["steps"]
+    assert 1 <= steps <= 1500 and t1.shape == (8, 2 * steps)
+    assert bool(torch.isfinite(dbg["logits"]).all())
+    assert int(t1.max()) <= cfg.semantic_eos_id and int(t1.min()) >= -1
+
+
+def test_t2s_argument_errors(dev, models):
+    m = models["cosingle"][1]["bf16"]
+    ids = syn.synthetic_text_ids(syn.COSINGLE, 1, 8)
+    with pytest.raises(NotImplementedError):
+        m.generate(ids, cond_scale=2.0)
+    with pytest.raises(NotImplementedError):
+        m.generate(ids, beam_search_decode=True)
+    with pytest.raises(ValueError):
+        m.generate(ids, max_length=8, noise=torch.rand(4, 1, 1, syn.COSINGLE.n_logits))
+    with pytest.raises(ValueError):
+        m.generate(torch.zeros(9, 4, dtype=torch.long), max_length=4)
