@@ -154,10 +154,13 @@ size_t covo_t2s_workspace_bytes(const covo_t2s* h, int B, int S, int max_length)
  *              [2] 1 if the kernel aborted on a stuck grid barrier
  *   logits_out f32 [max_length, n_out, B, n_logits] or NULL: pre-filter logits of every step
  *   enc_out    f32 [B, S, dim] or NULL: output of the source transformer (parity tests)
- *   top_k: ceil(0.1 * n_logits) = 51 for filter_logits_fn = top_k (:126-132). */
+ *   top_k: ceil(0.1 * n_logits) = 51 for filter_logits_fn = top_k (:126-132).
+ *   flags: COVO_T2S_IGNORE_EOS = never stop early (benchmarking on random weights, where EOS would end the loop at a
+ *          random position); 0 = the reference's rule. */
+enum { COVO_T2S_IGNORE_EOS = 1 };
 int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, const int64_t* forced, int64_t* tokens,
                       int32_t* result, float* logits_out, float* enc_out, int B, int S, int max_length, float temperature,
-                      int top_k, void* workspace, size_t workspace_bytes, void* stream);
+                      int top_k, int flags, void* workspace, size_t workspace_bytes, void* stream);
 /* Kernels launched by one covo_t2s_generate call (the whole autoregressive loop is one of them). */
 int covo_t2s_launches_per_generate(const covo_t2s* h);
 /* Bytes of decoder matrices one decoding step streams (the quantity the step is bound by). */

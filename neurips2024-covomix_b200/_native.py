@@ -48,6 +48,7 @@ class T2SCfg(C.Structure):
 
 
 COVO_T2S_W_BF16, COVO_T2S_W_F32 = 0, 1
+COVO_T2S_IGNORE_EOS = 1
 
 _lib = None
 
@@ -85,7 +86,7 @@ def lib() -> C.CDLL:
     L.covo_t2s_destroy.argtypes = [vp]
     L.covo_t2s_workspace_bytes.argtypes = [vp, i32, i32, i32]
     L.covo_t2s_workspace_bytes.restype = sz
-    L.covo_t2s_generate.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, sz, vp]
+    L.covo_t2s_generate.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, vp, sz, vp]
     L.covo_t2s_launches_per_generate.argtypes = [vp]
     L.covo_t2s_weight_bytes_per_step.argtypes = [vp]
     L.covo_t2s_weight_bytes_per_step.restype = sz

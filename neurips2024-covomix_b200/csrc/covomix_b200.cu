@@ -224,7 +224,8 @@ int covo_t2s_create(const covo_t2s_cfg* cfg, const void* packed_weights, size_t 
     if (cfg->dim_head != T2S_DH) return fail(COVO_ERR_INVALID, "dim_head=%d unsupported (64 only)", cfg->dim_head);
     if (cfg->target_depth < 1 || cfg->target_depth > T2S_MAX_DEPTH || cfg->source_depth < 0)
         return fail(COVO_ERR_INVALID, "target_depth=%d / source_depth=%d out of range", cfg->target_depth, cfg->source_depth);
-    if (cfg->dim % 8 || cfg->target_transformer_dim % 16 || cfg->heads < 1 || (cfg->num_semantic_token_ids + 1) % 2)
+    if (cfg->dim % 8 || cfg->target_transformer_dim % 16 || cfg->heads < 1 || (cfg->num_semantic_token_ids + 1) % 2 ||
+        cfg->num_semantic_token_ids + 1 > T2S_THREADS)
         return fail(COVO_ERR_INVALID, "unsupported dims (dim=%d, target dim=%d, heads=%d, semantic ids=%d)", cfg->dim,
                     cfg->target_transformer_dim, cfg->heads, cfg->num_semantic_token_ids);
     if (cfg->weight_format != COVO_T2S_W_BF16 && cfg->weight_format != COVO_T2S_W_F32)
@@ -276,7 +277,7 @@ size_t covo_t2s_weight_bytes_per_step(const covo_t2s* h) {
 
 int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, const int64_t* forced, int64_t* tokens,
                       int32_t* result, float* logits_out, float* enc_out, int B, int S, int max_length, float temperature,
-                      int top_k, void* workspace, size_t workspace_bytes, void* stream) {
+                      int top_k, int flags, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !text_ids || !u || !tokens || !result || !workspace) return fail(COVO_ERR_INVALID, "null argument");
     if (B != 1 && B != 2 && B != 4 && B != 8)
         return fail(COVO_ERR_INVALID, "B=%d: the decode kernel takes 1, 2, 4 or 8 rows (the host mirror pads)", B);
@@ -297,6 +298,7 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
 
     T2SDecArgs a;
     memset(&a, 0, sizeof(a));
+    int trace_step = -1;
     const int H = c.heads, n_ctx = S + 1;
     const size_t ctx_per = static_cast<size_t>(B) * H * n_ctx * T2S_DH, cache_per = static_cast<size_t>(B) * H * max_length * T2S_DH;
     for (int L = 0; L < c.target_depth; ++L) {
@@ -331,8 +333,21 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
     a.n_ctx = n_ctx;
     a.max_len = max_length;
     a.topk = top_k;
-    a.nsplit_self = a.nsplit_ctx = t2s_nsplit(h->di.num_sms, B, H);
+    {
+        const char* dm = getenv("COVO_T2S_DEBUG_SKIP");     // bit mask: 1 all work, 2 attention, 4 matrix products, 8 sampler, 16 no weight prefetch, 32 plain (not evict-first) weight loads
+        a.dbg_mode = dm ? atoi(dm) : 0;
+        const int skip_gemv = (a.dbg_mode & 4) ? 1 : 0;
+        COVO_CK(cudaMemcpyToSymbolAsync(t2s_dbg_skip_gemv, &skip_gemv, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+        const char* ts = getenv("COVO_T2S_TRACE");
+        trace_step = ts ? atoi(ts) : -1;
+        COVO_CK(cudaMemcpyToSymbolAsync(t2s_trace_step, &trace_step, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+        const int plain = (a.dbg_mode & 32) ? 1 : 0;
+        COVO_CK(cudaMemcpyToSymbolAsync(t2s_dbg_plain_loads, &plain, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+        const int no_pf = (a.dbg_mode & 16) ? 1 : 0;
+        COVO_CK(cudaMemcpyToSymbolAsync(t2s_dbg_no_prefetch, &no_pf, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    }
     a.temperature = temperature;
+    a.ignore_eos = (flags & COVO_T2S_IGNORE_EOS) ? 1 : 0;
     a.eos_id = c.num_semantic_token_ids;
     a.emb = h->dec_emb.as<float>();
     a.start = h->dec_start.as<float>();
@@ -341,7 +356,9 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
     a.ctx_mask = t.cmask;
     a.x = t.x;
     a.q = t.q;
+    a.attn = t.attn;
     a.part = t.part;
+    a.part_cnt = t.part_cnt;
     a.hbuf = t.hbuf;
     a.logits = t.logits;
     a.u = u;
@@ -351,7 +368,7 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
     a.result = t.result;
     a.eos_flags = t.eos_flags;
     a.barrier = t.barrier;
-    const size_t smem = t2s_decode_smem(h, B, n_ctx, max_length);
+    const size_t smem = t2s_decode_smem(h, B);
     {
         ProfScope ps(PC_T2S_DECODE, 0.0, st);
         int rc = COVO_OK;
@@ -368,6 +385,26 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
         COVO_TRY(rc);
     }
     COVO_CK(cudaMemcpyAsync(result, t.result, 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (trace_step >= 0) {      // debug only: synchronises
+        long long tb[128];
+        COVO_CK(cudaStreamSynchronize(st));
+        COVO_CK(cudaMemcpyFromSymbol(tb, t2s_trace_buf, sizeof(tb)));
+        static const char* names[21] = {"S1 norm", "S1 gemv", "S1 barrier", "S2 attn", "S2 barrier", "S3 load", "S3 gemv",
+                                        "S3 barrier", "S4 norm+gemv", "S4 barrier", "S5 attn", "S5 barrier", "S6 load+gemv",
+                                        "S6 barrier", "S7 norm", "S7 gemv", "S7 barrier", "S8 load", "S8 gemv", "S8 barrier", ""};
+        for (int L = 0; L < c.target_depth; ++L) {
+            fprintf(stderr, "[t2s trace] step %d layer %d (cycles):", trace_step, L);
+            for (int i = 0; i < 20; ++i) fprintf(stderr, " %s=%lld", names[i], tb[2 + L * 24 + i + 1] - tb[2 + L * 24 + i]);
+            fprintf(stderr, "\n");
+        }
+        for (int k = 0; k < 2; ++k) {
+            fprintf(stderr, "[t2s trace] layer 0 %s attention, CTA 0 (cycles since stage start):", k ? "cross" : "self");
+            for (int i = 1; i < 10; ++i) fprintf(stderr, " m%d=%lld", i, tb[106 + 10 * k + i] ? tb[106 + 10 * k + i] - tb[106 + 10 * k] : -1);
+            fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "[t2s trace] S9 logits=%lld barrier=%lld S10 sample=%lld barrier=%lld\n", tb[101] - tb[100],
+                tb[102] - tb[101], tb[103] - tb[102], tb[104] - tb[103]);
+    }
     return COVO_OK;
 }
 

@@ -135,19 +135,19 @@ __global__ void t2s_geglu_kernel(const float* __restrict__ h, float* __restrict_
     g[i] = gelu_erf(h[m * 2 * fi + fi + j]) * h[m * 2 * fi + j];
 }
 
-// kv [B*S1, 2*inner] of the encoded text + null_kv [2,H,1,64] -> ctx k / v [B][H][1+S1][64] (null first, :253-257);
+// kv [B*S1, 2*inner] of the encoded text + null_kv [2,H,64] -> ctx k / v [B][H][1+S1][64] (null first, :253-257);
 // cmask [B][1+S1] = 1 | source_mask (:259-260)
 __global__ void t2s_ctx_scatter_kernel(const float* __restrict__ kv, const float* __restrict__ null_kv,
                                        const uint8_t* __restrict__ mask, float* __restrict__ ck, float* __restrict__ cv,
                                        uint8_t* __restrict__ cmask, int B, int S1, int H) {
-    const int inner = H * T2S_DH;
-    const size_t n = static_cast<size_t>(B) * H * (S1 + 1) * T2S_DH;
+    const int inner = H * T2S_DH, n_ctx = S1 + 1;
+    const size_t n = static_cast<size_t>(B) * H * n_ctx * T2S_DH;
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int d = i % T2S_DH;
-    const int j = (i / T2S_DH) % (S1 + 1);
-    const int h = (i / (static_cast<size_t>(T2S_DH) * (S1 + 1))) % H;
-    const int b = i / (static_cast<size_t>(T2S_DH) * (S1 + 1) * H);
+    const int j = (i / T2S_DH) % n_ctx;
+    const int h = (i / (static_cast<size_t>(T2S_DH) * n_ctx)) % H;
+    const int b = i / (static_cast<size_t>(T2S_DH) * n_ctx * H);
     if (j == 0) {
         ck[i] = null_kv[h * T2S_DH + d];
         cv[i] = null_kv[(H + h) * T2S_DH + d];
@@ -156,12 +156,14 @@ __global__ void t2s_ctx_scatter_kernel(const float* __restrict__ kv, const float
         ck[i] = r[0];
         cv[i] = r[inner];
     }
-    if (h == 0 && d == 0) cmask[b * (S1 + 1) + j] = j == 0 ? 1 : mask[b * S1 + j - 1];
+    if (h == 0 && d == 0) cmask[b * n_ctx + j] = j == 0 ? 1 : mask[b * S1 + j - 1];
 }
 
 // ======================================================================================================================
 // the persistent decode kernel
 // ======================================================================================================================
+constexpr int T2S_MAXS = 64;          // max key splits per (b, h): one warp handles ~32 keys
+
 struct T2SLayerW {
     const float* sa_gamma;
     const void* sa_qkv;      // [3*inner, Dt]   rows: q | k | v   (to_q.0.weight ; to_kv.0.weight)
@@ -182,7 +184,7 @@ struct T2SLayerW {
 
 struct T2SDecArgs {
     T2SLayerW L[T2S_MAX_DEPTH];
-    int depth, B, Dt, inner, H, ffi, ffi_pad, n_out, demb, n_logits, n_ctx, max_len, topk, nsplit_self, nsplit_ctx;
+    int depth, B, Dt, inner, H, ffi, ffi_pad, n_out, demb, n_logits, n_ctx, max_len, topk, ignore_eos, dbg_mode;
     float temperature;
     long long eos_id;
     const float* emb;            // [n_logits, demb] fp32: input embedding and (tied) logit projection
@@ -192,7 +194,9 @@ struct T2SDecArgs {
     const uint8_t* ctx_mask;     // [B][n_ctx]
     float* x;                    // [B][Dt]   residual stream of the current position
     float* q;                    // [B][inner]
-    float* part;                 // [B*H*nsplit][66]
+    float* attn;                 // [B][inner]   merged attention output
+    float* part;                 // [B*H][T2S_MAXS][66]
+    unsigned* part_cnt;          // [B*H] arrival counters of the split merge
     float* hbuf;                 // [B][ffi_pad]   (padding columns stay zero)
     float* logits;               // [n_out][B][n_logits]
     const float* u;              // [max_len][n_out][B][n_logits]
@@ -204,35 +208,46 @@ struct T2SDecArgs {
     unsigned* barrier;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// All CTAs are co-resident (cooperative launch).  A stuck barrier sets the abort flag instead of hanging the device.
+// All CTAs are co-resident (cooperative launch).  Arrive = one red.release (orders this CTA's earlier writes, made visible to
+// thread 0 by the __syncthreads); wait = relaxed polling.  Every buffer another CTA wrote is read with __ldcg (L2), so no
+// gpu-scope acquire fence -- which would also throw away L1 -- is needed after the wait.  A stuck barrier sets the abort flag
+// instead of hanging the device.
 __device__ __forceinline__ bool t2s_grid_barrier(const T2SDecArgs& a, unsigned& epoch) {
     __shared__ int s_abort;
     __syncthreads();
     if (threadIdx.x == 0) {
         epoch += gridDim.x;
-        __threadfence();
-        atomicAdd(a.barrier, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.barrier), "r"(1u) : "memory");
         const long long t0 = clock64();
         int ab = 0;
-        while (ld_acquire_u32(a.barrier) < epoch) {
-            if (clock64() - t0 > 4000000000ll) {
+        unsigned v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barrier) : "memory");
+            if (v < epoch && clock64() - t0 > 4000000000ll) {
                 a.result[2] = 1;
                 ab = 1;
                 break;
             }
-        }
-        if (!ab) ab = *reinterpret_cast<volatile int*>(&a.result[2]);
-        s_abort = ab;
-        __threadfence();
+        } while (v < epoch);
+        s_abort = ab;       // a CTA that gives up leaves the others to their own time-out
     }
     __syncthreads();
     return s_abort != 0;
+}
+
+// 16-byte load of a decoder matrix.  The matrices are streamed once per decoding step (92 MB as bf16 -- three quarters of
+// L2); marking them evict-first keeps them from flushing the small, latency-critical working set (activations, KV cache,
+// cross-attention context) out of L2 every step.
+__device__ int t2s_dbg_plain_loads = 0;
+__device__ __forceinline__ uint4 t2s_ld_stream(const void* p) {
+    uint4 v;
+    if (t2s_dbg_plain_loads) return *reinterpret_cast<const uint4*>(p);
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
 }
 
 template <class WT>
@@ -241,7 +256,7 @@ template <>
 struct WVec<__nv_bfloat16> {
     static constexpr int N = 8;     // elements per 16-byte load
     __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&w)[8]) {
-        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        const uint4 v = t2s_ld_stream(p);
         const uint32_t r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -254,24 +269,60 @@ template <>
 struct WVec<float> {
     static constexpr int N = 4;
     __device__ static __forceinline__ void load(const float* p, float (&w)[4]) {
-        const float4 v = *reinterpret_cast<const float4*>(p);
-        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+        const uint4 v = t2s_ld_stream(p);
+        w[0] = __uint_as_float(v.x), w[1] = __uint_as_float(v.y), w[2] = __uint_as_float(v.z), w[3] = __uint_as_float(v.w);
     }
 };
 
-// Skinny product over row PAIRS: for pair p, rows r0 = base(p), r1 = r0 + pair_off of W [*, ldw] against the NB activation
-// rows sx[b][0..K) in shared memory; epi(r0, r1, acc0[NB], acc1[NB]) runs on lane 0 with the full sums.  Pairs are dealt
-// round-robin to all warps of the grid.  K is a multiple of WVec::N; W rows are 16-byte aligned.
-template <class WT, int NB, class Epi>
-__device__ __forceinline__ void t2s_gemv_pairs(const WT* __restrict__ W, int ldw, int n_pairs, int pair_stride,
-                                               int pair_off, int K, const float* sx, int ldx, Epi epi) {
+// debug tracer (COVO_T2S_TRACE=<step>): CTA 0 stamps clock64 at stage boundaries of one decoding step
+__device__ long long t2s_trace_buf[128];
+__device__ int t2s_trace_step = -1;
+#define T2S_MARK(id)                                                                              \
+    do {                                                                                          \
+        if (blockIdx.x == 0 && threadIdx.x == 0 && step == t2s_trace_step) t2s_trace_buf[id] = clock64(); \
+    } while (0)
+__device__ int t2s_dbg_no_prefetch = 0;
+__device__ int t2s_dbg_skip_gemv = 0;     // debug: time the kernel without the matrix products (tools/t2s_bench.py)
+
+template <int N>
+__device__ __forceinline__ float t2s_select(const float (&v)[N], int i) {
+    float r = v[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) r = (i == j) ? v[j] : r;
+    return r;
+}
+
+// Activation rows live in shared memory.  For 16-bit weights a lane's 16-byte weight load covers 8 consecutive k; the two
+// float4 halves of the matching activations are stored `half` = K/2 floats apart so that consecutive lanes read consecutive
+// 16-byte words (conflict-free; the linear layout is a 2-way bank conflict on every read, which bounds the B = 8 stages).
+// half == 0: linear layout (fp32 weights: 4 k per load).
+__device__ __forceinline__ int t2s_sx_index(int j, int half) {
+    return half ? ((((j >> 3) << 2) | (j & 3)) + ((j >> 2) & 1) * half) : j;
+}
+template <class WT>
+__device__ __forceinline__ int t2s_half(int K) {
+    return WVec<WT>::N == 8 ? K / 2 : 0;
+}
+
+// Skinny product: unit u covers R rows (r0 = u * unit_stride, r1 = r0 + pair_off when R == 2) of W [*, ldw] against the NB
+// activation rows in shared memory (layout t2s_sx_index with half = t2s_half<WT>(K)).  Units are dealt to the warps of the
+// grid CTA-interleaved, so stages with fewer units than warps still pull through every SM.  Lane b < NB first calls
+// pre(r0, r1, b) (a prefetch -- e.g. the residual -- issued BEFORE the weight loads so that its latency hides behind them)
+// and, once the sums are complete, epi(r0, r1, b, v0, v1, prefetched).  K % WVec::N == 0; W rows are 16-byte aligned.
+template <class WT, int NB, int R, class Pre, class Epi>
+__device__ __forceinline__ void t2s_gemv(const WT* __restrict__ W, int ldw, int n_units, int unit_stride, int pair_off, int K,
+                                         const float* sx, int ldx, Pre pre, Epi epi) {
     constexpr int VN = WVec<WT>::N;
     const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * T2S_WARPS + (threadIdx.x >> 5);
+    const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     const int GW = gridDim.x * T2S_WARPS;
     const int chunks = K / VN;
-    for (int p = gw; p < n_pairs; p += GW) {
-        const int r0 = p * pair_stride, r1 = r0 + pair_off;
+    const int half = t2s_half<WT>(K);
+    if (t2s_dbg_skip_gemv) n_units = 0;
+    for (int u = gw; u < n_units; u += GW) {
+        const int r0 = u * unit_stride, r1 = r0 + pair_off;
+        float2 pf = make_float2(0.f, 0.f);
+        if (lane < NB) pf = pre(r0, r1, lane);
         const WT* w0p = W + static_cast<size_t>(r0) * ldw;
         const WT* w1p = W + static_cast<size_t>(r1) * ldw;
         float acc0[NB], acc1[NB];
@@ -281,21 +332,22 @@ __device__ __forceinline__ void t2s_gemv_pairs(const WT* __restrict__ W, int ldw
         for (int c = lane; c < chunks; c += 32) {
             float w0[VN], w1[VN];
             WVec<WT>::load(w0p + c * VN, w0);
-            WVec<WT>::load(w1p + c * VN, w1);
+            if (R == 2) WVec<WT>::load(w1p + c * VN, w1);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const float* xb = sx + b * ldx + c * VN;
 #pragma unroll
                 for (int i = 0; i < VN; i += 4) {
-                    const float4 xv = *reinterpret_cast<const float4*>(xb + i);
+                    const float4 xv = *reinterpret_cast<const float4*>(sx + b * ldx + c * 4 + (i ? half : 0));
                     acc0[b] = fmaf(w0[i], xv.x, acc0[b]);
                     acc0[b] = fmaf(w0[i + 1], xv.y, acc0[b]);
                     acc0[b] = fmaf(w0[i + 2], xv.z, acc0[b]);
                     acc0[b] = fmaf(w0[i + 3], xv.w, acc0[b]);
-                    acc1[b] = fmaf(w1[i], xv.x, acc1[b]);
-                    acc1[b] = fmaf(w1[i + 1], xv.y, acc1[b]);
-                    acc1[b] = fmaf(w1[i + 2], xv.z, acc1[b]);
-                    acc1[b] = fmaf(w1[i + 3], xv.w, acc1[b]);
+                    if (R == 2) {
+                        acc1[b] = fmaf(w1[i], xv.x, acc1[b]);
+                        acc1[b] = fmaf(w1[i + 1], xv.y, acc1[b]);
+                        acc1[b] = fmaf(w1[i + 2], xv.z, acc1[b]);
+                        acc1[b] = fmaf(w1[i + 3], xv.w, acc1[b]);
+                    }
                 }
             }
         }
@@ -304,200 +356,359 @@ __device__ __forceinline__ void t2s_gemv_pairs(const WT* __restrict__ W, int ldw
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 acc0[b] += __shfl_xor_sync(0xffffffffu, acc0[b], o);
-                acc1[b] += __shfl_xor_sync(0xffffffffu, acc1[b], o);
+                if (R == 2) acc1[b] += __shfl_xor_sync(0xffffffffu, acc1[b], o);
             }
         }
-        if (lane == 0) epi(r0, r1, acc0, acc1);
+        if (lane < NB) epi(r0, r1, lane, t2s_select<NB>(acc0, lane), t2s_select<NB>(acc1, lane), pf);
     }
 }
 
-// sx[b][0..D) = RMSNorm(x[b]) * gamma  (text2semantic.py:143-151); x is written by other CTAs -> L2 loads (__ldcg)
+// A plain projection (no row pairing needed): two adjacent rows per unit when NB >= 4 (halves the shared-memory reads per
+// FMA, which is what bounds the wide-batch stages), one row per unit otherwise (more warps, shorter chains).
+// epi1(r, b, v, prefetched) / pre1(r, b) see single rows.
+template <class WT, int NB, class Pre1, class Epi1>
+__device__ __forceinline__ void t2s_gemv_rows(const WT* __restrict__ W, int ldw, int n_rows, int K, const float* sx, int ldx,
+                                              Pre1 pre1, Epi1 epi1) {
+    if (NB >= 4) {
+        t2s_gemv<WT, NB, 2>(W, ldw, n_rows / 2, 2, 1, K, sx, ldx,
+                            [=](int r0, int r1, int b) { return make_float2(pre1(r0, b), pre1(r1, b)); },
+                            [=](int r0, int r1, int b, float v0, float v1, float2 pf) {
+                                epi1(r0, b, v0, pf.x);
+                                epi1(r1, b, v1, pf.y);
+                            });
+    } else {
+        t2s_gemv<WT, NB, 1>(W, ldw, n_rows, 1, 0, K, sx, ldx, [=](int r0, int, int b) { return make_float2(pre1(r0, b), 0.f); },
+                            [=](int r0, int, int b, float v0, float, float2 pf) { epi1(r0, b, v0, pf.x); });
+    }
+}
+
+// Ask L2 for the weight rows this warp will use in the NEXT stage before waiting at the grid barrier: the rows do not
+// depend on the activations, so an HBM miss overlaps the barrier and the activation load.  (L1 would be the better target
+// but gpu-scope fences invalidate it.)
+__device__ __forceinline__ void t2s_prefetch_rows(const void* W, int row_bytes, int n_units, int unit_stride, int pair_off,
+                                                  int R) {
+    if (t2s_dbg_no_prefetch) return;
+    const int lane = threadIdx.x & 31;
+    const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, GW = gridDim.x * T2S_WARPS;
+    const char* base = static_cast<const char*>(W);
+    for (int u = gw; u < n_units; u += GW) {
+        for (int r = 0; r < R; ++r) {
+            const char* row = base + static_cast<size_t>(u * unit_stride + r * pair_off) * row_bytes;
+            for (int off = lane * 128; off < row_bytes; off += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+        }
+    }
+}
+template <class WT, int NB>
+__device__ __forceinline__ void t2s_prefetch_plain(const void* W, int ldw, int n_rows) {
+    if (NB >= 4) t2s_prefetch_rows(W, ldw * static_cast<int>(sizeof(WT)), n_rows / 2, 2, 1, 2);
+    else t2s_prefetch_rows(W, ldw * static_cast<int>(sizeof(WT)), n_rows, 1, 0, 1);
+}
+
+// sx[b][idx(j)] = x[b][j] * gamma[j];  sscale[b] = sqrt(D) / max(||x[b]||, 1e-12).  RMSNorm (text2semantic.py:143-151) is
+// x / ||x|| * sqrt(D) * gamma; the per-row factor commutes with the matrix product that follows, so it is applied to the
+// sums in the epilogue (no second pass over the row).  x is written by other CTAs -> L2 loads (__ldcg).  D % 4 == 0.
 template <int NB>
-__device__ __forceinline__ void t2s_load_norm(const float* x, const float* __restrict__ gamma, int D, float* sx, int ldx,
-                                              float* sred) {
+__device__ __forceinline__ void t2s_load_norm(const float* x, const float* __restrict__ gamma, int D, int half, float* sx,
+                                              int ldx, float* sred, float* sscale) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float ss[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        ss[b] = 0.f;
-        for (int j = tid; j < D; j += T2S_THREADS) {
-            const float v = __ldcg(x + b * D + j);
-            sx[b * ldx + j] = v;
-            ss[b] = fmaf(v, v, ss[b]);
+    for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+    for (int j = tid * 4; j < D; j += T2S_THREADS * 4) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + j);
+        float4 v[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b] = __ldcg(reinterpret_cast<const float4*>(x + b * D + j));
+        const int dst = t2s_sx_index(j, half);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            *reinterpret_cast<float4*>(sx + b * ldx + dst) = make_float4(v[b].x * g.x, v[b].y * g.y, v[b].z * g.z, v[b].w * g.w);
+            ss[b] = fmaf(v[b].x, v[b].x, fmaf(v[b].y, v[b].y, fmaf(v[b].z, v[b].z, fmaf(v[b].w, v[b].w, ss[b]))));
         }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
         if (lane == 0) sred[b * T2S_WARPS + warp] = ss[b];
     }
     __syncthreads();
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    if (tid < NB) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < T2S_WARPS; ++w) t += sred[b * T2S_WARPS + w];
-        const float scale = sqrtf(static_cast<float>(D)) / fmaxf(sqrtf(t), 1e-12f);
-        for (int j = tid; j < D; j += T2S_THREADS) sx[b * ldx + j] *= scale * gamma[j];
+        for (int w = 0; w < T2S_WARPS; ++w) t += sred[tid * T2S_WARPS + w];
+        sscale[tid] = sqrtf(static_cast<float>(D)) / fmaxf(sqrtf(t), 1e-12f);
     }
     __syncthreads();
 }
 
-// One (b, h, split) unit of single-query attention: q [64] against keys [k0, k1) of K/V [n_alloc][64] -> partial (m, l, o).
-// Scores use masked_fill(-FLT_MAX) like the reference (attend_t2s.py:151-153).
-__device__ __forceinline__ void t2s_attn_unit(const float* q, const float* K, const float* V, const uint8_t* mask, int k0,
-                                              int k1, float* part, float* sq, float* sc, float* sred, float* so) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < T2S_DH) sq[tid] = __ldcg(q + tid) * 0.125f;        // dim_head ** -0.5
-    __syncthreads();
-    const int nk = k1 - k0;
-    float mx = -3.402823466e38f;
-    for (int j = tid; j < nk; j += T2S_THREADS) {
-        const float4* kr = reinterpret_cast<const float4*>(K + static_cast<size_t>(k0 + j) * T2S_DH);
-        float s = 0.f;
-#pragma unroll
-        for (int d = 0; d < T2S_DH / 4; ++d) {
-            const float4 kv = __ldcg(kr + d);
-            s = fmaf(sq[4 * d], kv.x, s);
-            s = fmaf(sq[4 * d + 1], kv.y, s);
-            s = fmaf(sq[4 * d + 2], kv.z, s);
-            s = fmaf(sq[4 * d + 3], kv.w, s);
-        }
-        if (mask != nullptr && !mask[k0 + j]) s = -3.402823466e38f;
-        sc[j] = s;
-        mx = fmaxf(mx, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) sred[warp] = mx;
-    __syncthreads();
-    mx = sred[0];
-#pragma unroll
-    for (int w = 1; w < T2S_WARPS; ++w) mx = fmaxf(mx, sred[w]);
-    __syncthreads();
-    float sum = 0.f;
-    for (int j = tid; j < nk; j += T2S_THREADS) {
-        const float p = expf(sc[j] - mx);
-        sc[j] = p;
-        sum += p;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) sred[warp] = sum;
-    __syncthreads();
-    sum = 0.f;
-#pragma unroll
-    for (int w = 0; w < T2S_WARPS; ++w) sum += sred[w];
-    // o = sum_j p_j V[j]: warps stride over keys, a lane owns dims (2 lane, 2 lane + 1) -> 256-byte coalesced rows
-    float2 acc = make_float2(0.f, 0.f);
-    for (int j = warp; j < nk; j += T2S_WARPS) {
-        const float2 vv = __ldcg(reinterpret_cast<const float2*>(V + static_cast<size_t>(k0 + j) * T2S_DH) + lane);
-        const float p = sc[j];
-        acc.x = fmaf(p, vv.x, acc.x);
-        acc.y = fmaf(p, vv.y, acc.y);
-    }
-    so[warp * T2S_DH + 2 * lane] = acc.x;
-    so[warp * T2S_DH + 2 * lane + 1] = acc.y;
-    __syncthreads();
-    if (tid < T2S_DH) {
-        float o = 0.f;
-#pragma unroll
-        for (int w = 0; w < T2S_WARPS; ++w) o += so[w * T2S_DH + tid];
-        part[2 + tid] = o;
-    }
-    if (tid == 0) {
-        part[0] = nk > 0 ? mx : -3.402823466e38f;
-        part[1] = nk > 0 ? sum : 0.f;
-    }
-    __syncthreads();
-}
-
-// sx[b][h*64 + d] = merged attention output of the nsplit partials of (b, h)
+// sx[b][idx(j)] = src[b][j], j < n  (an activation other CTAs produced; n % 4 == 0)
 template <int NB>
-__device__ __forceinline__ void t2s_combine(const float* part, int H, int nsplit, float* sx, int ldx) {
-    for (int i = threadIdx.x; i < NB * H * T2S_DH; i += T2S_THREADS) {
-        const int d = i % T2S_DH, bh = i / T2S_DH;
-        const float* p = part + static_cast<size_t>(bh) * nsplit * T2S_PART;
-        float M = -3.402823466e38f;
-        for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(p + s * T2S_PART));
-        float l = 0.f, o = 0.f;
-        for (int s = 0; s < nsplit; ++s) {
-            const float ls = __ldcg(p + s * T2S_PART + 1);
-            if (ls > 0.f) {
-                const float w = expf(__ldcg(p + s * T2S_PART) - M);
-                l = fmaf(ls, w, l);
-                o = fmaf(__ldcg(p + s * T2S_PART + 2 + d), w, o);
+__device__ __forceinline__ void t2s_load_plain(const float* src, int n, int half, float* sx, int ldx) {
+    const int n4 = n / 4;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < NB * n4; i += T2S_THREADS) {
+        const int b = i / n4, j = (i - b * n4) * 4;
+        *reinterpret_cast<float4*>(sx + b * ldx + t2s_sx_index(j, half)) = __ldcg(reinterpret_cast<const float4*>(src + b * n + j));
+    }
+    __syncthreads();
+}
+
+// Single-query attention stage (attend_t2s.py:127-171 with one query row).  A CTA owns a unit = (b, h, group of up to 16
+// consecutive 32-key blocks); warp w takes block w: a lane owns one key for the score (its 256-byte K row: 16 independent
+// 16-byte loads), the warp takes max / sum with shuffles, then a lane owns two output dims and the 32 V rows are read
+// coalesced with the probabilities broadcast by shuffle -- all loads of a block are independent, so a block costs about one
+// memory round trip.  The warps' (m, l, o[64]) are merged in shared memory.  The group size is chosen so that the units just
+// fill the grid; when one group covers all keys (always for the cross attention, and for the first 512 positions of the
+// self attention at B = 8) the result goes straight to attn[b][h*64 ...]; otherwise the CTA writes a partial and the last CTA
+// to arrive for (b, h) merges the partials -- no extra grid barrier either way.  Masked keys score -FLT_MAX like the
+// reference's masked_fill (attend_t2s.py:151-153).
+__device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB, const float* Kc, const float* Vc, int n_alloc,
+                                                    int nkeys, const uint8_t* mask, float* sq, float* spart, int* sflag, int trace_base) {
+#define T2S_AMARK(id)                                                                                  \
+    do {                                                                                              \
+        if (trace_base >= 0 && blockIdx.x == 0 && threadIdx.x == 0) t2s_trace_buf[trace_base + (id)] = clock64(); \
+    } while (0)
+    T2S_AMARK(0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblocks = (nkeys + 31) / 32;
+    const int BH = NB * a.H;
+    // blocks per group: the 16 warps of a CTA work in parallel, so a full group costs no more latency than one block and
+    // saves the cross-CTA merge; groups are only made smaller when that is needed to give every SM a unit
+    int bpg = nblocks < T2S_WARPS ? nblocks : T2S_WARPS;
+    while (bpg > 4 && BH * ((nblocks + bpg - 1) / bpg) * 2 <= static_cast<int>(gridDim.x) && nblocks > bpg) bpg >>= 1;
+    const int ngroups = (nblocks + bpg - 1) / bpg;                                              // <= T2S_MAXS
+    const int units = BH * ngroups;
+    constexpr float NEG = -3.402823466e38f;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int g = u % ngroups, bh = u / ngroups, b = bh / a.H;
+        if (tid < T2S_DH / 2) {
+            const float2 qv = __ldcg(reinterpret_cast<const float2*>(a.q + static_cast<size_t>(bh) * T2S_DH) + tid);
+            sq[2 * tid] = qv.x * 0.125f;            // dim_head ** -0.5
+            sq[2 * tid + 1] = qv.y * 0.125f;
+        }
+        __syncthreads();
+        T2S_AMARK(1);
+        const int kb = (g * bpg + warp) * 32;
+        float m = NEG, l = 0.f;
+        float2 o = make_float2(0.f, 0.f);
+        if (warp < bpg && kb < nkeys) {
+            const float* Kb = Kc + static_cast<size_t>(bh) * n_alloc * T2S_DH;
+            const float* Vb = Vc + static_cast<size_t>(bh) * n_alloc * T2S_DH;
+            const int j = kb + lane;
+            const int cnt = min(32, nkeys - kb);
+            float sc = NEG;
+            if (j < nkeys) {
+                const float4* kr = reinterpret_cast<const float4*>(Kb + static_cast<size_t>(j) * T2S_DH);
+                float4 kv[T2S_DH / 4];
+#pragma unroll
+                for (int d = 0; d < T2S_DH / 4; ++d) kv[d] = __ldcg(kr + d);
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < T2S_DH / 4; ++d) {
+                    const float4 qq = *reinterpret_cast<const float4*>(sq + 4 * d);
+                    acc = fmaf(qq.x, kv[d].x, acc);
+                    acc = fmaf(qq.y, kv[d].y, acc);
+                    acc = fmaf(qq.z, kv[d].z, acc);
+                    acc = fmaf(qq.w, kv[d].w, acc);
+                }
+                sc = (mask != nullptr && !mask[b * a.n_ctx + j]) ? NEG : acc;
+            }
+            T2S_AMARK(2);
+            m = sc;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+            const float p = j < nkeys ? expf(sc - m) : 0.f;
+            l = p;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+            T2S_AMARK(3);
+            const float2* vr = reinterpret_cast<const float2*>(Vb + static_cast<size_t>(kb) * T2S_DH) + lane;
+            if (cnt == 32) {
+                float2 vv[32];
+#pragma unroll
+                for (int t = 0; t < 32; ++t) vv[t] = __ldcg(vr + t * (T2S_DH / 2));
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const float pt = __shfl_sync(0xffffffffu, p, t);
+                    o.x = fmaf(pt, vv[t].x, o.x);
+                    o.y = fmaf(pt, vv[t].y, o.y);
+                }
+            } else {
+                for (int t = 0; t < cnt; ++t) {
+                    const float2 vv = __ldcg(vr + t * (T2S_DH / 2));
+                    const float pt = __shfl_sync(0xffffffffu, p, t);
+                    o.x = fmaf(pt, vv.x, o.x);
+                    o.y = fmaf(pt, vv.y, o.y);
+                }
             }
         }
-        sx[(bh / H) * ldx + (bh % H) * T2S_DH + d] = o / l;
+        T2S_AMARK(4);
+        float* sp = spart + warp * T2S_PART;
+        if (lane == 0) sp[0] = m, sp[1] = l;
+        *reinterpret_cast<float2*>(sp + 2 + 2 * lane) = o;
+        __syncthreads();
+        T2S_AMARK(5);
+        // merge the warps' partials: thread d < 64 owns output dim d
+        float Mg = NEG, Lg = 0.f, og = 0.f;
+        const int nw = min(bpg, nblocks - g * bpg);
+        if (tid < T2S_DH) {
+            for (int w = 0; w < nw; ++w) Mg = fmaxf(Mg, spart[w * T2S_PART]);
+            for (int w = 0; w < nw; ++w) {
+                const float lw = spart[w * T2S_PART + 1];
+                const float wt = lw > 0.f ? expf(spart[w * T2S_PART] - Mg) : 0.f;
+                Lg = fmaf(lw, wt, Lg);
+                og = fmaf(spart[w * T2S_PART + 2 + tid], wt, og);
+            }
+        }
+        if (ngroups == 1) {
+            if (tid < T2S_DH) a.attn[static_cast<size_t>(bh) * T2S_DH + tid] = og / Lg;
+            __syncthreads();
+            T2S_AMARK(6);
+            continue;
+        }
+        float* part = a.part + (static_cast<size_t>(bh) * T2S_MAXS + g) * T2S_PART;
+        if (tid < T2S_DH) {
+            part[2 + tid] = og;
+            if (tid == 0) part[0] = Mg, part[1] = Lg;
+            __threadfence();
+        }
+        __syncthreads();
+        T2S_AMARK(7);
+        if (tid == 0) sflag[0] = atomicAdd(a.part_cnt + bh, 1u) == static_cast<unsigned>(ngroups - 1);
+        __syncthreads();
+        T2S_AMARK(8);
+        if (sflag[0] && tid < T2S_DH) {
+            __threadfence();
+            const float* pb = a.part + static_cast<size_t>(bh) * T2S_MAXS * T2S_PART;
+            // all loads first (independent), then the max / weighted sum
+            float M2 = NEG, L2 = 0.f, o2 = 0.f;
+            for (int t0 = 0; t0 < ngroups; t0 += 8) {
+                float mt[8], lt[8], pv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool ok = t0 + i < ngroups;
+                    const float* pp = pb + (ok ? t0 + i : t0) * T2S_PART;
+                    mt[i] = __ldcg(pp);
+                    lt[i] = ok ? __ldcg(pp + 1) : 0.f;
+                    pv[i] = __ldcg(pp + 2 + tid);
+                }
+                float Mn = M2;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Mn = lt[i] > 0.f ? fmaxf(Mn, mt[i]) : Mn;
+                const float r = L2 > 0.f ? expf(M2 - Mn) : 0.f;
+                L2 *= r;
+                o2 *= r;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float wt = lt[i] > 0.f ? expf(mt[i] - Mn) : 0.f;
+                    L2 = fmaf(lt[i], wt, L2);
+                    o2 = fmaf(pv[i], wt, o2);
+                }
+                M2 = Mn;
+            }
+            a.attn[static_cast<size_t>(bh) * T2S_DH + tid] = o2 / L2;
+            if (tid == 0) a.part_cnt[bh] = 0u;       // next use is behind at least one grid barrier
+        }
+        __syncthreads();
+        T2S_AMARK(9);
     }
-    __syncthreads();
+#undef T2S_AMARK
 }
 
-template <int NB>
-__device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, const float* Kb, const float* Vb, int n_alloc,
-                                                    int nkeys, int nsplit, const uint8_t* mask, int mask_ld, float* sq,
-                                                    float* sc, float* sred, float* so) {
-    const int units = NB * a.H * nsplit;
-    const int per = (nkeys + nsplit - 1) / nsplit;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int s = u % nsplit, bh = u / nsplit, b = bh / a.H;
-        const int k0 = min(s * per, nkeys), k1 = min(k0 + per, nkeys);
-        t2s_attn_unit(a.q + static_cast<size_t>(bh) * T2S_DH, Kb + static_cast<size_t>(bh) * n_alloc * T2S_DH,
-                      Vb + static_cast<size_t>(bh) * n_alloc * T2S_DH, mask ? mask + b * mask_ld : nullptr, k0, k1,
-                      a.part + static_cast<size_t>(u) * T2S_PART, sq, sc, sred, so);
-    }
+// Monotone map float -> uint32 (larger float <=> larger key), for the radix select below
+__device__ __forceinline__ unsigned t2s_sortable(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
 // top-k filter + Gumbel arg-max for one (stream, batch row) (text2semantic.py:104-132, :793-800); also feeds the next
-// position: x[b][s*demb ...] = emb[token]  (:746-751)
-__device__ __forceinline__ void t2s_sample_unit(const T2SDecArgs& a, int s, int b, int step, float* sl, float* sval,
+// position: x[b][s*demb ...] = emb[token]  (:746-751).  The k-th largest logit is found by a 4-pass radix select over the
+// order-preserving integer image of the logits (shared-memory histograms); logits >= it survive the filter (torch.topk keeps
+// exactly k: identical unless two logits tie bit-for-bit at the threshold).
+__device__ __forceinline__ void t2s_sample_unit(const T2SDecArgs& a, int s, int b, int step, unsigned* hist, float* sval,
                                                 int* sidx) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = a.n_logits;
+    const int n = a.n_logits;                         // <= T2S_THREADS (checked on the host)
     const size_t off = (static_cast<size_t>(s) * a.B + b) * n;
-    for (int r = tid; r < n; r += T2S_THREADS) {
-        const float l = __ldcg(a.logits + off + r);
-        sl[r] = l;
-        if (a.logits_out != nullptr) a.logits_out[static_cast<size_t>(step) * a.n_out * a.B * n + off + r] = l;
+    float l = -INFINITY, g = 0.f;
+    long long fed = -1;
+    if (tid < n) {
+        l = __ldcg(a.logits + off + tid);
+        const float uu = a.u[static_cast<size_t>(step) * a.n_out * a.B * n + off + tid];
+        g = -logf(fmaxf(-logf(fmaxf(uu, 1e-20f)), 1e-20f));
+        if (a.logits_out != nullptr) a.logits_out[static_cast<size_t>(step) * a.n_out * a.B * n + off + tid] = l;
     }
-    __syncthreads();
+    if (tid == 0 && a.forced != nullptr) fed = a.forced[(static_cast<size_t>(b) * a.n_out + s) * a.max_len + step];
+    const unsigned key = tid < n ? t2s_sortable(l) : 0u;
+    unsigned prefix = 0u, pmask = 0u;
+    int want = a.topk;                                // rank (1-based, from the top) still to locate inside the prefix class
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (tid < 256) hist[tid] = 0u;
+        __syncthreads();
+        if (tid < n && (key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        __syncthreads();
+        if (warp == 0) {                              // find the bin (from the top) where the cumulative count reaches `want`
+            unsigned c[8], tot = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                c[i] = hist[255 - (lane * 8 + i)];
+                tot += c[i];
+            }
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            unsigned run = incl - tot;                // elements in higher bins
+            int found = -1, rem = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (found < 0 && run + c[i] >= static_cast<unsigned>(want)) {
+                    found = 255 - (lane * 8 + i);
+                    rem = want - static_cast<int>(run);
+                }
+                run += c[i];
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, found >= 0);
+            const int src = __ffs(ball) - 1;          // lowest lane = highest bins
+            found = __shfl_sync(0xffffffffu, found, src);
+            rem = __shfl_sync(0xffffffffu, rem, src);
+            if (lane == 0) sidx[0] = found, sidx[1] = rem;
+        }
+        __syncthreads();
+        prefix |= static_cast<unsigned>(sidx[0]) << shift;
+        pmask |= 255u << shift;
+        want = sidx[1];
+        __syncthreads();
+    }
+    // prefix == key of the k-th largest logit
     float best = -INFINITY;
     int best_i = 0x7fffffff;
-    for (int r = tid; r < n; r += T2S_THREADS) {
-        const float l = sl[r];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const float o = sl[j];
-            rank += (o > l) || (o == l && j < r);
-        }
-        if (rank < a.topk) {
-            const float uu = a.u[static_cast<size_t>(step) * a.n_out * a.B * n + off + r];
-            const float g = -logf(fmaxf(-logf(fmaxf(uu, 1e-20f)), 1e-20f));
-            const float v = l / fmaxf(a.temperature, 1e-10f) + g;
-            if (v > best || (v == best && r < best_i)) best = v, best_i = r;
-        }
-    }
+    if (tid < n && key >= prefix) best = l / fmaxf(a.temperature, 1e-10f) + g, best_i = tid;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
         if (ov > best || (ov == best && oi < best_i)) best = ov, best_i = oi;
     }
-    if (lane == 0) sval[warp] = best, sidx[warp] = best_i;
+    if (lane == 0) sval[warp] = best, sidx[2 + warp] = best_i;
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < T2S_WARPS; ++w)
-            if (sval[w] > best || (sval[w] == best && sidx[w] < best_i)) best = sval[w], best_i = sidx[w];
+            if (sval[w] > best || (sval[w] == best && sidx[2 + w] < best_i)) best = sval[w], best_i = sidx[2 + w];
         if (best_i >= n) best_i = 0;               // only reachable with non-finite logits
         a.tokens[(static_cast<size_t>(b) * a.n_out + s) * a.max_len + step] = best_i;
-        if (best_i == a.eos_id) a.eos_flags[s * a.B + b] = 1;
-        sidx[0] = best_i;
+        if (best_i == a.eos_id && !a.ignore_eos) a.eos_flags[s * a.B + b] = 1;
+        if (a.forced == nullptr) fed = best_i;
+        if (fed < 0 || fed >= n) fed = a.eos_id;   // pad (-1) after EOS: never reached for B = 1 (see t2s.py)
+        sidx[0] = static_cast<int>(fed);
     }
     __syncthreads();
-    long long fed = sidx[0];
-    if (a.forced != nullptr) fed = a.forced[(static_cast<size_t>(b) * a.n_out + s) * a.max_len + step];
-    if (fed < 0 || fed >= n) fed = a.eos_id;       // pad (-1) after EOS: never reached for B = 1 (see t2s.py)
-    for (int j = tid; j < a.demb; j += T2S_THREADS)
-        a.x[static_cast<size_t>(b) * a.Dt + s * a.demb + j] = a.emb[static_cast<size_t>(fed) * a.demb + j];
+    const float* e = a.emb + static_cast<size_t>(sidx[0]) * a.demb;
+    for (int j = tid; j < a.demb; j += T2S_THREADS) a.x[static_cast<size_t>(b) * a.Dt + s * a.demb + j] = e[j];
     __syncthreads();
 }
 
@@ -506,162 +717,162 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
     extern __shared__ __align__(16) float smem[];
     const int ldx = a.ffi_pad > a.Dt ? a.ffi_pad : a.Dt;
     float* sx = smem;                                  // [NB][ldx]
-    float* sc = sx + NB * ldx;                         // [max(max_len, n_ctx, n_logits) + 8]
-    const int sc_n = ((max(max(a.max_len, a.n_ctx), a.n_logits) + 8) + 3) & ~3;
-    float* sq = sc + sc_n;                             // [64]
+    float* spart = sx + NB * ldx;                      // [16 warps][66]  (also the sampler's 256-bin histogram)
+    float* sq = spart + T2S_WARPS * T2S_PART;          // [64]
     float* sred = sq + T2S_DH;                         // [NB * 16]
-    float* so = sred + NB * T2S_WARPS;                 // [16][64]
-    int* sidx = reinterpret_cast<int*>(so + T2S_WARPS * T2S_DH);   // [16]
+    float* sscale = sred + NB * T2S_WARPS;             // [8]
+    int* sidx = reinterpret_cast<int*>(sscale + 8);    // [2 + 16]
     unsigned epoch = 0;
     const int tid = threadIdx.x;
-    const WT* dummy = nullptr;
-    (void)dummy;
+    const int Dt = a.Dt, inner = a.inner;
+    float* const x = a.x;
+    const auto no_pre = [](int, int, int) { return make_float2(0.f, 0.f); };
+    const auto no_pre1 = [](int, int) { return 0.f; };
+    const auto resid = [=](int r, int b) { return __ldcg(x + b * Dt + r); };
 
     // position 0 input: the start token (text2semantic.py:746-751)
-    for (int i = blockIdx.x * T2S_THREADS + tid; i < NB * a.Dt; i += gridDim.x * T2S_THREADS) a.x[i] = a.start[i % a.Dt];
+    for (int i = blockIdx.x * T2S_THREADS + tid; i < NB * Dt; i += gridDim.x * T2S_THREADS) a.x[i] = a.start[i % Dt];
     if (t2s_grid_barrier(a, epoch)) return;
 
     for (int step = 0; step < a.max_len; ++step) {
         for (int L = 0; L < a.depth; ++L) {
             const T2SLayerW& w = a.L[L];
+            const bool work = (a.dbg_mode & 1) == 0;
+            const int mk = 2 + L * 24;
+            T2S_MARK(mk + 0);
             // ---- S1: self-attention q | k | v of the new position; rotary at position `step`; k, v appended to the cache
-            t2s_load_norm<NB>(a.x, w.sa_gamma, a.Dt, sx, ldx, sred);
-            {
+            if (work) {
+                t2s_load_norm<NB>(a.x, w.sa_gamma, Dt, t2s_half<WT>(Dt), sx, ldx, sred, sscale);
+                T2S_MARK(mk + 1);
                 const float2* rope = a.rope + static_cast<size_t>(step) * (T2S_DH / 2);
-                const int inner = a.inner, H = a.H, max_len = a.max_len;
+                const int H = a.H, max_len = a.max_len;
                 float* qb = a.q;
                 float* kc = w.kcache;
                 float* vc = w.vcache;
-                t2s_gemv_pairs<WT, NB>(static_cast<const WT*>(w.sa_qkv), a.Dt, 3 * inner / 2, 2, 1, a.Dt, sx, ldx,
-                                       [=](int r0, int, const float* a0, const float* a1) {
-                                           const int sect = r0 / inner, c = r0 % inner, h = c / T2S_DH, d = c % T2S_DH;
-                                           const float2 cs = rope[d >> 1];
-#pragma unroll
-                                           for (int b = 0; b < NB; ++b) {
-                                               float v0 = a0[b], v1 = a1[b];
-                                               if (sect < 2) {
-                                                   const float t0 = v0 * cs.x - v1 * cs.y;
-                                                   v1 = v1 * cs.x + v0 * cs.y;
-                                                   v0 = t0;
-                                               }
-                                               if (sect == 0) {
-                                                   qb[b * inner + c] = v0;
-                                                   qb[b * inner + c + 1] = v1;
-                                               } else {
-                                                   float* dst = (sect == 1 ? kc : vc) +
-                                                                ((static_cast<size_t>(b) * H + h) * max_len + step) * T2S_DH + d;
-                                                   dst[0] = v0;
-                                                   dst[1] = v1;
-                                               }
-                                           }
-                                       });
+                t2s_gemv<WT, NB, 2>(static_cast<const WT*>(w.sa_qkv), Dt, 3 * inner / 2, 2, 1, Dt, sx, ldx, no_pre,
+                                    [=](int r0, int, int b, float v0, float v1, float2) {
+                                        const int sect = r0 / inner, c = r0 % inner, h = c / T2S_DH, d = c % T2S_DH;
+                                        v0 *= sscale[b];
+                                        v1 *= sscale[b];
+                                        if (sect < 2) {
+                                            const float2 cs = rope[d >> 1];
+                                            const float t0 = v0 * cs.x - v1 * cs.y;
+                                            v1 = v1 * cs.x + v0 * cs.y;
+                                            v0 = t0;
+                                        }
+                                        if (sect == 0) {
+                                            *reinterpret_cast<float2*>(qb + b * inner + c) = make_float2(v0, v1);
+                                        } else {
+                                            float* dst = (sect == 1 ? kc : vc) +
+                                                         ((static_cast<size_t>(b) * H + h) * max_len + step) * T2S_DH + d;
+                                            *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                                        }
+                                    });
+                t2s_prefetch_plain<WT, NB>(w.sa_out, inner, Dt);
             }
+            T2S_MARK(mk + 2);
             if (t2s_grid_barrier(a, epoch)) return;
+            T2S_MARK(mk + 3);
             // ---- S2: causal self-attention of the one query over the step + 1 cached keys
-            t2s_attention_stage<NB>(a, w.kcache, w.vcache, a.max_len, step + 1, a.nsplit_self, nullptr, 0, sq, sc, sred, so);
+            if (work && !(a.dbg_mode & 2))
+                t2s_attention_stage(a, NB, w.kcache, w.vcache, a.max_len, step + 1, nullptr, sq, spart, sidx,
+                                    (L == 0 && step == t2s_trace_step) ? 106 : -1);
+            T2S_MARK(mk + 4);
             if (t2s_grid_barrier(a, epoch)) return;
+            T2S_MARK(mk + 5);
             // ---- S3: to_out + residual
-            t2s_combine<NB>(a.part, a.H, a.nsplit_self, sx, ldx);
-            {
-                float* x = a.x;
-                const int Dt = a.Dt;
-                t2s_gemv_pairs<WT, NB>(static_cast<const WT*>(w.sa_out), a.inner, a.Dt / 2, 2, 1, a.inner, sx, ldx,
-                                       [=](int r0, int r1, const float* a0, const float* a1) {
-#pragma unroll
-                                           for (int b = 0; b < NB; ++b) {
-                                               x[b * Dt + r0] = a0[b] + __ldcg(x + b * Dt + r0);
-                                               x[b * Dt + r1] = a1[b] + __ldcg(x + b * Dt + r1);
-                                           }
-                                       });
+            if (work) {
+                t2s_load_plain<NB>(a.attn, inner, t2s_half<WT>(inner), sx, ldx);
+                T2S_MARK(mk + 6);
+                t2s_gemv_rows<WT, NB>(static_cast<const WT*>(w.sa_out), inner, Dt, inner, sx, ldx, resid,
+                                      [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
+                t2s_prefetch_plain<WT, NB>(w.ca_q, Dt, inner);
             }
+            T2S_MARK(mk + 7);
             if (t2s_grid_barrier(a, epoch)) return;
+            T2S_MARK(mk + 8);
             // ---- S4: cross-attention query
-            t2s_load_norm<NB>(a.x, w.ca_gamma, a.Dt, sx, ldx, sred);
-            {
+            if (work) {
+                t2s_load_norm<NB>(a.x, w.ca_gamma, Dt, t2s_half<WT>(Dt), sx, ldx, sred, sscale);
                 float* qb = a.q;
-                const int inner = a.inner;
-                t2s_gemv_pairs<WT, NB>(static_cast<const WT*>(w.ca_q), a.Dt, a.inner / 2, 2, 1, a.Dt, sx, ldx,
-                                       [=](int r0, int r1, const float* a0, const float* a1) {
-#pragma unroll
-                                           for (int b = 0; b < NB; ++b) {
-                                               qb[b * inner + r0] = a0[b];
-                                               qb[b * inner + r1] = a1[b];
-                                           }
-                                       });
+                t2s_gemv_rows<WT, NB>(static_cast<const WT*>(w.ca_q), Dt, inner, Dt, sx, ldx, no_pre1,
+                                      [=](int r, int b, float v, float) { qb[b * inner + r] = v * sscale[b]; });
+                t2s_prefetch_plain<WT, NB>(w.ca_out, inner, Dt);
             }
+            T2S_MARK(mk + 9);
             if (t2s_grid_barrier(a, epoch)) return;
+            T2S_MARK(mk + 10);
             // ---- S5: cross attention over [null kv | encoded text] with the source padding mask
-            t2s_attention_stage<NB>(a, w.ctx_k, w.ctx_v, a.n_ctx, a.n_ctx, a.nsplit_ctx, a.ctx_mask, a.n_ctx, sq, sc, sred, so);
+            if (work && !(a.dbg_mode & 2))
+                t2s_attention_stage(a, NB, w.ctx_k, w.ctx_v, a.n_ctx, a.n_ctx, a.ctx_mask, sq, spart, sidx,
+                                    (L == 0 && step == t2s_trace_step) ? 116 : -1);
+            T2S_MARK(mk + 11);
             if (t2s_grid_barrier(a, epoch)) return;
+            T2S_MARK(mk + 12);
             // ---- S6: to_out + residual
-            t2s_combine<NB>(a.part, a.H, a.nsplit_ctx, sx, ldx);
-            {
-                float* x = a.x;
-                const int Dt = a.Dt;
-                t2s_gemv_pairs<WT, NB>(static_cast<const WT*>(w.ca_out), a.inner, a.Dt / 2, 2, 1, a.inner, sx, ldx,
-                                       [=](int r0, int r1, const float* a0, const float* a1) {
-#pragma unroll
-                                           for (int b = 0; b < NB; ++b) {
-                                               x[b * Dt + r0] = a0[b] + __ldcg(x + b * Dt + r0);
-                                               x[b * Dt + r1] = a1[b] + __ldcg(x + b * Dt + r1);
-                                           }
-                                       });
+            if (work) {
+                t2s_load_plain<NB>(a.attn, inner, t2s_half<WT>(inner), sx, ldx);
+                t2s_gemv_rows<WT, NB>(static_cast<const WT*>(w.ca_out), inner, Dt, inner, sx, ldx, resid,
+                                      [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
+                t2s_prefetch_rows(w.ff1, Dt * static_cast<int>(sizeof(WT)), a.ffi, 1, a.ffi, 2);
             }
+            T2S_MARK(mk + 13);
             if (t2s_grid_barrier(a, epoch)) return;
+            T2S_MARK(mk + 14);
             // ---- S7: FF in-projection + GEGLU: row i (x part) is paired with row ffi + i (gate)
-            t2s_load_norm<NB>(a.x, w.ff_gamma, a.Dt, sx, ldx, sred);
-            {
+            if (work) {
+                t2s_load_norm<NB>(a.x, w.ff_gamma, Dt, t2s_half<WT>(Dt), sx, ldx, sred, sscale);
+                T2S_MARK(mk + 15);
                 float* hb = a.hbuf;
                 const float* b1 = w.ff1_b;
-                const int ffi = a.ffi, ffi_pad = a.ffi_pad;
-                t2s_gemv_pairs<WT, NB>(static_cast<const WT*>(w.ff1), a.Dt, a.ffi, 1, a.ffi, a.Dt, sx, ldx,
-                                       [=](int r0, int r1, const float* a0, const float* a1) {
-                                           const float bx = b1[r0], bg = b1[r1];
-#pragma unroll
-                                           for (int b = 0; b < NB; ++b)
-                                               hb[b * ffi_pad + r0] = gelu_erf(a1[b] + bg) * (a0[b] + bx);
-                                           (void)ffi;
-                                       });
+                const int ffi_pad = a.ffi_pad;
+                t2s_gemv<WT, NB, 2>(static_cast<const WT*>(w.ff1), Dt, a.ffi, 1, a.ffi, Dt, sx, ldx,
+                                    [=](int r0, int r1, int) { return make_float2(b1[r0], b1[r1]); },
+                                    [=](int r0, int, int b, float v0, float v1, float2 pf) {
+                                        hb[b * ffi_pad + r0] = gelu_erf(fmaf(v1, sscale[b], pf.y)) * fmaf(v0, sscale[b], pf.x);
+                                    });
+                t2s_prefetch_plain<WT, NB>(w.ff2, ffi_pad, Dt);
             }
+            T2S_MARK(mk + 16);
             if (t2s_grid_barrier(a, epoch)) return;
+            T2S_MARK(mk + 17);
             // ---- S8: FF out-projection + bias + residual
-            for (int i = tid; i < NB * a.ffi_pad; i += T2S_THREADS)
-                sx[(i / a.ffi_pad) * ldx + i % a.ffi_pad] = __ldcg(a.hbuf + i);
-            __syncthreads();
-            {
-                float* x = a.x;
+            if (work) {
+                t2s_load_plain<NB>(a.hbuf, a.ffi_pad, t2s_half<WT>(a.ffi_pad), sx, ldx);
+                T2S_MARK(mk + 18);
                 const float* b2 = w.ff2_b;
-                const int Dt = a.Dt;
-                t2s_gemv_pairs<WT, NB>(static_cast<const WT*>(w.ff2), a.ffi_pad, a.Dt / 2, 2, 1, a.ffi_pad, sx, ldx,
-                                       [=](int r0, int r1, const float* a0, const float* a1) {
-#pragma unroll
-                                           for (int b = 0; b < NB; ++b) {
-                                               x[b * Dt + r0] = a0[b] + b2[r0] + __ldcg(x + b * Dt + r0);
-                                               x[b * Dt + r1] = a1[b] + b2[r1] + __ldcg(x + b * Dt + r1);
-                                           }
-                                       });
+                t2s_gemv_rows<WT, NB>(static_cast<const WT*>(w.ff2), a.ffi_pad, Dt, a.ffi_pad, sx, ldx,
+                                      [=](int r, int b) { return __ldcg(x + b * Dt + r) + b2[r]; },
+                                      [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
+                if (L + 1 < a.depth) t2s_prefetch_rows(a.L[L + 1].sa_qkv, Dt * static_cast<int>(sizeof(WT)), 3 * inner / 2, 2, 1, 2);
+                else t2s_prefetch_plain<float, NB>(a.emb, a.demb, a.n_logits);
             }
+            T2S_MARK(mk + 19);
             if (t2s_grid_barrier(a, epoch)) return;
+            T2S_MARK(mk + 20);
         }
+        T2S_MARK(100);
         // ---- S9: final norm + tied logit projection per output stream (text2semantic.py:762-776), fp32 table
-        t2s_load_norm<NB>(a.x, a.final_gamma, a.Dt, sx, ldx, sred);
-        for (int s = 0; s < a.n_out; ++s) {
-            float* lg = a.logits + static_cast<size_t>(s) * NB * a.n_logits;
-            const int n = a.n_logits;
-            t2s_gemv_pairs<float, NB>(a.emb, a.demb, a.n_logits / 2, 2, 1, a.demb, sx + s * a.demb, ldx,
-                                      [=](int r0, int r1, const float* a0, const float* a1) {
-#pragma unroll
-                                          for (int b = 0; b < NB; ++b) {
-                                              lg[b * n + r0] = a0[b];
-                                              lg[b * n + r1] = a1[b];
-                                          }
-                                      });
+        if ((a.dbg_mode & 1) == 0) {
+            t2s_load_norm<NB>(a.x, a.final_gamma, Dt, 0, sx, ldx, sred, sscale);
+            for (int s = 0; s < a.n_out; ++s) {
+                float* lg = a.logits + static_cast<size_t>(s) * NB * a.n_logits;
+                const int n = a.n_logits;
+                t2s_gemv_rows<float, NB>(a.emb, a.demb, a.n_logits, a.demb, sx + s * a.demb, ldx, no_pre1,
+                                         [=](int r, int b, float v, float) { lg[b * n + r] = v * sscale[b]; });
+            }
+            t2s_prefetch_rows(a.L[0].sa_qkv, Dt * static_cast<int>(sizeof(WT)), 3 * inner / 2, 2, 1, 2);
         }
+        T2S_MARK(101);
         if (t2s_grid_barrier(a, epoch)) return;
+        T2S_MARK(102);
         // ---- S10: sampling, one CTA per (stream, row); writes the next position's input embedding
-        for (int u = blockIdx.x; u < a.n_out * NB; u += gridDim.x)
-            t2s_sample_unit(a, u / NB, u % NB, step, sc, sred, sidx);
+        if (!(a.dbg_mode & 8))
+            for (int u = blockIdx.x; u < a.n_out * NB; u += gridDim.x)
+                t2s_sample_unit(a, u / NB, u % NB, step, reinterpret_cast<unsigned*>(spart), sred, sidx);
+        T2S_MARK(103);
         if (t2s_grid_barrier(a, epoch)) return;
+        T2S_MARK(104);
         // ---- EOS logic (text2semantic.py:804-826): stop when every row of stream 1 -- or, with two outputs, every row
         // of either stream -- has produced an EOS
         bool stop = false;
@@ -677,7 +888,6 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
         if (stop) break;
     }
 }
-
 
 struct T2SEncLayerW {
     Tensor attn_gamma, q_w, kv_w, out_w, ff_gamma, ff1_w, ff1_b, ff2_w, ff2_b;
@@ -763,17 +973,9 @@ inline int t2s_bind_weights(covo_t2s* h) {
 
 inline int t2s_pad_batch(int B) { return B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8)); }
 
-inline int t2s_nsplit(int num_sms, int B, int H) {
-    int s = num_sms / (B * H);
-    return s < 1 ? 1 : (s > 16 ? 16 : s);
-}
-
-inline size_t t2s_decode_smem(const covo_t2s* h, int NB, int n_ctx, int max_len) {
+inline size_t t2s_decode_smem(const covo_t2s* h, int NB) {
     const int ldx = h->ffi_pad > h->cfg.target_transformer_dim ? h->ffi_pad : h->cfg.target_transformer_dim;
-    int sc_n = max_len > n_ctx ? max_len : n_ctx;
-    if (h->n_logits > sc_n) sc_n = h->n_logits;
-    sc_n = (sc_n + 8 + 3) & ~3;
-    return sizeof(float) * (static_cast<size_t>(NB) * ldx + sc_n + T2S_DH + NB * T2S_WARPS + T2S_WARPS * T2S_DH + T2S_WARPS);
+    return sizeof(float) * (static_cast<size_t>(NB) * ldx + T2S_WARPS * T2S_PART + T2S_DH + NB * T2S_WARPS + 8 + 2 + T2S_WARPS + 2);
 }
 
 // Workspace layout for (B rows padded to NB, S1 text positions incl. EOS, max_len decode positions)
@@ -784,9 +986,9 @@ struct T2SBuffers {
     float *xe, *he, *qe, *kve, *ae, *f1e, *ge, *tmp;
     float2* rope;
     // decode
-    float *ctx_k, *ctx_v, *kcache, *vcache, *x, *q, *part, *hbuf, *logits;
+    float *ctx_k, *ctx_v, *kcache, *vcache, *x, *q, *attn, *part, *hbuf, *logits;
     int *result, *eos_flags;
-    unsigned* barrier;
+    unsigned *barrier, *part_cnt;
     size_t zero_from = 0, zero_bytes = 0;     // region cleared before every call
 };
 
@@ -796,7 +998,6 @@ inline size_t t2s_layout(const covo_t2s* h, int NB, int S1, int max_len, void* w
     const size_t M = static_cast<size_t>(NB) * S1;
     const int n_ctx = S1 + 1, H = c.heads;
     const int rope_n = max_len > S1 ? max_len : S1;
-    const int nsplit = t2s_nsplit(h->di.num_sms, NB, H);
     T2SBuffers t;
     t.ids = a.take<long long>(M);
     t.mask = a.take<uint8_t>(M);
@@ -818,7 +1019,8 @@ inline size_t t2s_layout(const covo_t2s* h, int NB, int S1, int max_len, void* w
     t.vcache = a.take<float>(cache_n);
     t.x = a.take<float>(static_cast<size_t>(NB) * c.target_transformer_dim);
     t.q = a.take<float>(static_cast<size_t>(NB) * h->inner);
-    t.part = a.take<float>(static_cast<size_t>(NB) * H * nsplit * T2S_PART);
+    t.attn = a.take<float>(static_cast<size_t>(NB) * h->inner);
+    t.part = a.take<float>(static_cast<size_t>(NB) * H * T2S_MAXS * T2S_PART);
     t.logits = a.take<float>(static_cast<size_t>(h->n_out) * NB * h->n_logits);
     a.off = align_up(a.off, 256);
     t.zero_from = a.off;
@@ -826,6 +1028,7 @@ inline size_t t2s_layout(const covo_t2s* h, int NB, int S1, int max_len, void* w
     t.result = a.take<int>(4);
     t.eos_flags = a.take<int>(static_cast<size_t>(h->n_out) * NB);
     t.barrier = a.take<unsigned>(4);
+    t.part_cnt = a.take<unsigned>(static_cast<size_t>(NB) * H);
     t.zero_bytes = a.off - t.zero_from;
     if (b) *b = t;
     return align_up(a.off, 256);

@@ -121,10 +121,11 @@ class B200TextToSemantic:
     def generate(self, source, *, source_type="text", target_type="speech", temperature=1., filter_thres=0.1,
                  source_mask=None, max_length=2048, beam_search_decode=False, spec_decode=False,
                  return_source=False, return_target_mask=False, cond_scale=1., prompt_mel=None,
-                 noise: Optional[torch.Tensor] = None, forced: Optional[torch.Tensor] = None, return_debug=False):
+                 noise: Optional[torch.Tensor] = None, forced: Optional[torch.Tensor] = None, return_debug=False,
+                 ignore_eos=False):
         """``TextToSemantic.generate`` (text2semantic.py:659-848).  Extra keyword arguments (not in the reference):
         ``noise`` uniform draws [>=max_length, n_out, B, n_logits]; ``forced`` int64 [B, n_out, max_length] teacher
-        forcing; ``return_debug`` additionally returns a dict with per-step logits, the encoder output and the raw
+        forcing; ``ignore_eos`` never stops early (benchmarking); ``return_debug`` additionally returns a dict with per-step logits, the encoder output and the raw
         token / step counters."""
         if source_type != "text" or target_type != "speech":
             raise NotImplementedError("covomix_b200: only the text -> speech direction is on this path")
@@ -172,6 +173,7 @@ class B200TextToSemantic:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(nat.lib().covo_t2s_generate(self._h, _ptr(ids), _ptr(noise), _ptr(forced), _ptr(tokens), _ptr(result),
                                               _ptr(logits), _ptr(enc), NB, S1, max_length, float(temperature), k,
+                                              nat.COVO_T2S_IGNORE_EOS if ignore_eos else 0,
                                               _ptr(ws), ws.numel(), C.c_void_p(stream)), "covo_t2s_generate")
         steps, stopped, aborted = (int(v) for v in result[:3].tolist())           # one D2H sync, as the reference's loop
         if aborted:
