@@ -9,6 +9,8 @@ One "step" = one pass of the hot path over one batch of synthetic input:
         B = 8 dialogues of 30 s (N = 1650 frames = 150 prompt + 1500 generated), cond_scale 0.7,
         followed by the HiFi-GAN generator on the 8 x [80, 1500] generated mels -> 8 x 240032 samples.
     workload c2: VoSingle, 32 Euler steps, 10 s monologue (N = 650), B = 1, + vocoder.
+    workload c4: the full pipeline per GPU (BASELINE.json configs[3]): CoMix text-to-semantic -> VoMix -> vocoder.
+    workload c5: HiFi-GAN sweep (one JSON line per point).
 value = B * 30 s * n_gpus / seconds-per-step (whole job, inputs resident in HBM).
 e2e   = the same through the public Python API with pinned HOST inputs and a device->host read of the waveform.
 
@@ -36,6 +38,10 @@ WORKLOADS = {
                name="C3: VoMix 2-stream, 64 Euler steps (128 network passes), 30 s dialogue, batch 8, + HiFi-GAN"),
     "c2": dict(model="vosingle", B=1, N=650, prompt=150, method="euler", n_steps=32,
                name="C2: VoSingle, 32 Euler steps, 10 s monologue, batch 1, + HiFi-GAN"),
+    # BASELINE.json configs[3] per GPU: the full pipeline.  CoMix text-to-semantic (200 text tokens -> 1500 positions x 2
+    # streams, EOS ignored: random-init weights would stop at a random position) -> VoMix (as C3) -> HiFi-GAN.
+    "c4": dict(model="vomix", B=8, N=1650, prompt=150, method="euler", n_steps=64, t2s=dict(S=200, steps=1500),
+               name="C4 (per GPU): CoMix T2S (1500 AR steps, 2 streams) -> VoMix 64 Euler steps -> HiFi-GAN, 30 s dialogues, batch 8"),
 }
 
 
@@ -180,10 +186,14 @@ def run_reference(args):
     tv /= steps
     th /= steps
     sec_per_step = wl["B"] * (n_eval * tv + th)
+    if "t2s" in wl:
+        sec_per_step += wl["B"] * wl["t2s"]["steps"] * cpu_t2s_step_seconds(wl)
     audio_s = wl["B"] * gen_frames / FRAME_RATE
     value = audio_s / sec_per_step
     sample = (f"1 of {wl['B']} items, 1 of {n_eval} CFG velocity evaluations ({tv:.2f} s) + vocoder on 1 item ({th:.2f} s), "
               f"{steps} reps; step time extrapolated = B*(n_eval*t_eval + t_voc)")
+    if "t2s" in wl:
+        sample += f" + B*{wl['t2s']['steps']} text-to-semantic decoding steps timed on a 48-step sample (oracle, B = 1)"
     line = {
         "impl": "reference", "metric": "audio-seconds/sec (RTF)", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
@@ -229,8 +239,24 @@ def run_b200(args):
     ids_d, cond_d, y0_d = ids_h.to(dev), cond_h.to(dev), y0_h.to(dev)
     ids_p, cond_p = ids_h.pin_memory(), cond_h.pin_memory()
 
+    t2s = text_d = text_p = None
+    if "t2s" in wl:
+        from covomix_b200.t2s import B200TextToSemantic
+        t2s = B200TextToSemantic(syn.synthetic_t2s_state_dict(syn.COMIX, 1234), syn.COMIX, dev)
+        text_h = syn.synthetic_text_ids(syn.COMIX, B, wl["t2s"]["S"], seed=40 + rank, ragged=True)
+        text_d, text_p = text_h.to(dev), text_h.pin_memory()
+        assert wl["t2s"]["steps"] == gen_frames
+
+    def semantic_ids(text, prompt_ids):
+        """comix_pred + the id assembly of dialogue_generation.py:306-313: the two generated streams follow the prompt's."""
+        L = wl["t2s"]["steps"]
+        tgt = t2s.generate(text, max_length=L, ignore_eos=True)                  # [B, 2L]: stream 1 | stream 2
+        new = torch.stack((tgt[:, :L], tgt[:, L:]), dim=-1).clamp_(min=0, max=501)
+        return torch.cat((prompt_ids[:, :prompt], new), dim=1)
+
     def step_device():
-        mel = sampler.sample(phoneme_ids=ids_d, cond=cond_d, cond_scale=0.7, y0=y0_d)
+        ids = semantic_ids(text_d, ids_d) if t2s is not None else ids_d
+        mel = sampler.sample(phoneme_ids=ids, cond=cond_d, cond_scale=0.7, y0=y0_d)
         voc_in = mel[:, prompt:, :].permute(0, 2, 1)           # what the scripts do: sampled[:, mask].permute(0,2,1)
         return gen(voc_in)
 
@@ -239,6 +265,8 @@ def run_b200(args):
     def step_e2e():
         i = ids_p.to(dev, non_blocking=True)
         c = cond_p.to(dev, non_blocking=True)
+        if t2s is not None:
+            i = semantic_ids(text_p.to(dev, non_blocking=True), i)
         mel = sampler.sample(phoneme_ids=i, cond=c, cond_scale=0.7)   # y0 = torch.randn_like on device, as the reference
         wav = gen(mel[:, prompt:, :].permute(0, 2, 1))
         wav_host.copy_(wav, non_blocking=True)
@@ -278,7 +306,7 @@ def run_b200(args):
     ms_e2e_total, _ = timed(step_e2e, K, 1)
     ms_e2e = ms_e2e_total / K
     e2e_value = audio_s_per_step * world / (ms_e2e / 1e3)
-    h2d = ids_p.numel() * 8 + cond_p.numel() * 4
+    h2d = ids_p.numel() * 8 + cond_p.numel() * 4 + (text_p.numel() * 8 if text_p is not None else 0)
     d2h = wav_host.numel() * 4
 
     line = None
@@ -325,6 +353,17 @@ def run_b200(args):
                            "frac_of_peak": (flow_fl + voc_fl) / (ms_step * 1e-3) / 1e12 / pk["tflops"]},
         }
         launches = (sampler.launches_per_sample(0.7) + gen.launches_per_forward()) * K
+        t2s_info = None
+        if t2s is not None:
+            launches += t2s.launches_per_generate() * K
+            d_ms = pr["t2s_decode"][0]
+            steps_t = wl["t2s"]["steps"]
+            gbs = t2s.weight_bytes_per_step() * steps_t / (d_ms * 1e-3) / 1e9 if d_ms else None
+            t2s_info = {"kernel": "t2s_decode_kernel (persistent cooperative kernel, whole AR loop in one launch)",
+                        "ms": d_ms, "us_per_step": d_ms * 1e3 / steps_t, "tokens_per_s": B * 2 * steps_t / (d_ms * 1e-3) if d_ms else None,
+                        "bound": "latency (34 grid barriers per step) over weight streaming",
+                        "weight_bytes_per_step": t2s.weight_bytes_per_step(), "weight_stream_gbs": gbs,
+                        "frac_of_hbm_peak": gbs / pk["hbm"] if gbs else None, "share_of_step_kernel_time": d_ms / total_kernel_ms}
 
         # ---- CPU baseline on this box's host cores (oracle port, bounded sample)
         cpu = None
@@ -342,6 +381,8 @@ def run_b200(args):
                     "ms_per_step": ms_e2e},
             "ode_step_ms": ode_step_ms, "roofline": roofline,
         }
+        if t2s_info is not None:
+            line["t2s"] = t2s_info
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -428,10 +469,35 @@ def cpu_baseline(wl, cfg):
     orc.hifigan_forward(hsd, syn.HIFIGAN_COVOMIX, mel)
     th = time.perf_counter() - t0
     sec = wl["B"] * (n_eval * tv + th)
+    extra = ""
+    if "t2s" in wl:
+        tt = cpu_t2s_step_seconds(wl)
+        sec += wl["B"] * wl["t2s"]["steps"] * tt
+        extra = f" + {tt * 1e3:.1f} ms per text-to-semantic decoding step (oracle, B = 1, 64 cached positions) x {wl['t2s']['steps']} steps"
     return {"value": wl["B"] * gen_frames / FRAME_RATE / sec, "unit": "audio-s/s", "cores": cores, "kind": "port",
             "sample": f"1 of {wl['B']} items, 1 of {n_eval} CFG velocity evaluations ({tv:.2f} s, fp32 torch CPU) + vocoder on 1 item "
-                      f"({th:.2f} s); extrapolated linearly to the full step",
+                      f"({th:.2f} s){extra}; extrapolated linearly to the full step",
             "ode_step_ms_b1": tv * 1e3}
+
+
+def cpu_t2s_step_seconds(wl):
+    """Seconds per decoding step of the text-to-semantic oracle (B = 1, as the scripts run it) on the host cores:
+    bounded sample of 48 steps after a 16-step warm-up (the reference's own step also re-projects the cross-attention
+    context and re-embeds the prefix, so this is a lower bound for it)."""
+    from covomix_b200 import synthetic as syn
+    from oracle import t2s_oracle as t2o
+    sd = syn.synthetic_t2s_state_dict(syn.COMIX, 1234)
+    ids = syn.synthetic_text_ids(syn.COMIX, 1, wl["t2s"]["S"], seed=40, ragged=False)
+    with torch.inference_mode():
+        enc, mask = t2o.encode(sd, syn.COMIX, ids)
+        st = t2o.DecoderState(sd, syn.COMIX, enc, mask)
+        x = sd["start_token.speech"].expand(1, 1, -1)
+        for _ in range(16):
+            st.step(x)
+        t0 = time.perf_counter()
+        for _ in range(48):
+            st.step(x)
+        return (time.perf_counter() - t0) / 48
 
 
 def main():

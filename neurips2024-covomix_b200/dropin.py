@@ -5,6 +5,8 @@ The reference has no plugin layer on this path; the boundary is two Python call 
     model.synthesis_sample(phoneme_ids=, cond=, mask=, cond_scale=)   conditional_model.py:295-302
         -> self.cfm_wrapper.sample(...)                                 acoustic.py:597-688
     generator(mel)                                                       hifi-gan/models.py:100-116
+(and, one stage upstream, ``text2semantic.synthesis_sample_text2semantic(ids)`` -> ``cfm_wrapper.sample``,
+conditional_model.py:313-321 -> text2semantic.py:1237-1251, swapped by ``accelerate_text2semantic``).
 ``accelerate_acoustic_model`` swaps ``model.cfm_wrapper.sample`` for the B200 sampler built from the
 model's own (EMA-swapped, eval-mode) weights; ``accelerate_generator`` returns a callable with the
 Generator's interface built from the live generator's state dict.  Scripts, checkpoints and tensor
@@ -15,7 +17,7 @@ from __future__ import annotations
 import torch
 
 from .flow import B200FlowSampler
-from .packing import flow_config_from_state_dict
+from .packing import flow_config_from_state_dict, t2s_config_from_state_dict
 from .synthetic import HifiganConfig
 from .vocoder import B200Generator
 
@@ -36,6 +38,25 @@ def accelerate_acoustic_model(model, device=None, heads: int = 16, dim_head: int
     wrapper._b200_sampler = sampler
     wrapper._reference_sample = wrapper.sample
     wrapper.sample = sampler.sample               # same keyword signature as acoustic.py:598-607
+    return model
+
+
+def accelerate_text2semantic(model, device=None, heads: int = 8, dim_head: int = 64, weight_format: str = "bf16"):
+    """``model``: the text-to-semantic ``CoVoMixModel`` (``--t2s_ckpt``; ``.cfm_wrapper`` is a ``TextToSemanticWrapper``,
+    conditional_model.py:136).  Swaps ``model.cfm_wrapper.sample`` -- what ``synthesis_sample_text2semantic``
+    (conditional_model.py:313-321; ``comix_pred`` / ``cosingle_pred`` in the generation scripts) calls -- for
+    ``B200TextToSemantic.sample`` (same keyword signature, same flattened id tensor)."""
+    from .t2s import B200TextToSemantic
+    wrapper = model.cfm_wrapper
+    net = wrapper.model
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    if device is None:
+        device = next(net.parameters()).device
+    cfg = t2s_config_from_state_dict(sd, heads=heads, dim_head=dim_head)
+    t2s = B200TextToSemantic(sd, cfg, device, weight_format=weight_format)
+    wrapper._b200_t2s = t2s
+    wrapper._reference_sample = wrapper.sample
+    wrapper.sample = t2s.sample                   # text2semantic.py:1237-1251
     return model
 
 

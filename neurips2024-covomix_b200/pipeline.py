@@ -48,3 +48,32 @@ def synthesize(sampler, generator, items: Sequence[Dict[str, torch.Tensor]], con
 def concat_turns(turns: Sequence[np.ndarray]) -> np.ndarray:
     """dialogue_generation.py:189: per-turn audio of `--mode covosingle` dialogues is concatenated."""
     return np.concatenate(list(turns)) if len(turns) else np.zeros(0, dtype=np.int16)
+
+
+def comix_pred(t2s, text_ids: torch.Tensor, **kw):
+    """``comix_pred`` (dialogue_generation.py:332-344 == monologue_generation.py:307-319) on top of
+    ``B200TextToSemantic.sample``: one tokenised text -> the two semantic streams (first / second half of the flattened
+    output, exactly the reference's split) and the empty ``mel_to_synthesis`` placeholder."""
+    semantic = t2s.sample(text_ids.reshape(1, -1), **kw).reshape(-1).cpu()
+    half = semantic.shape[0] // 2
+    s1, s2 = semantic[:half], semantic[half:]
+    return s1, s2, torch.zeros((80, len(s1)))
+
+
+def dialogue_item(semantic_a: torch.Tensor, semantic_b: torch.Tensor, mel_prompt: torch.Tensor, new_a: torch.Tensor,
+                  new_b: torch.Tensor, pad_id: int = 157, max_id: int = 501) -> Dict[str, torch.Tensor]:
+    """The id / cond / mask assembly of ``covomix(...)`` (dialogue_generation.py:307-321): prompt streams followed by the
+    generated ones, right-padded with id 157 to a common length, clamped to 501; ``cond`` carries the prompt mel and zeros;
+    ``mask`` selects the generated frames."""
+    n_prompt = mel_prompt.shape[0]
+    a = torch.cat((semantic_a[:n_prompt], new_a))
+    b = torch.cat((semantic_b[:n_prompt], new_b))
+    n = max(a.shape[0], b.shape[0])
+    a = torch.nn.functional.pad(a, (0, n - a.shape[0]), value=pad_id)
+    b = torch.nn.functional.pad(b, (0, n - b.shape[0]), value=pad_id)
+    ids = torch.stack((a, b), dim=-1).clamp(max=max_id)
+    mask = torch.zeros(n, dtype=torch.bool)
+    mask[n_prompt:] = True
+    cond = torch.zeros(n, mel_prompt.shape[1])
+    cond[:n_prompt] = mel_prompt
+    return {"phoneme_ids": ids, "cond": cond, "mask": mask}

@@ -121,3 +121,73 @@ def test_synthesize_groups_equal_lengths_and_keeps_order():
         expect = mel.sum(0, keepdim=True).repeat_interleave(4, dim=1).to(torch.int16).numpy().reshape(-1)
         assert w.dtype == np.int16 and np.array_equal(w, expect)
     assert pipeline.concat_turns([wavs[1], wavs[4]]).shape[0] == wavs[1].shape[0] + wavs[4].shape[0]
+
+
+# ---------------------------------------------------------------------------------------------- text-to-semantic host logic
+def test_t2s_finish_targets_matches_oracle_loop_semantics():
+    """What the reference's loop leaves in target / target2 (text2semantic.py:804-832), for every exit path."""
+    from covomix_b200 import synthetic as syn
+    from covomix_b200.t2s import finish_targets, set_eos_id
+    from oracle import t2s_oracle as orc
+    eos = syn.COMIX.semantic_eos_id
+    tok = torch.tensor([[[5, eos, 7, 8], [9, 10, eos, 12]]])                 # [B=1, 2 streams, 4 steps]
+    # two outputs, loop exhausted (no break): stream 1 masked after its EOS, stream 2 untouched
+    t, m = finish_targets(tok, 4, False, syn.COMIX)
+    assert t.tolist() == [[5, eos, -1, -1, 9, 10, eos, 12]] and m.tolist() == [[1, 1, 0, 0, 1, 1, 1, 1]]
+    # two outputs, EOS rule fired: both masked
+    t, _ = finish_targets(tok, 4, True, syn.COMIX)
+    assert t.tolist() == [[5, eos, -1, -1, 9, 10, eos, -1]]
+    # one output: masked only when the EOS rule fired
+    t, _ = finish_targets(tok[:, :1], 4, False, syn.COSINGLE)
+    assert t.tolist() == [[5, eos, 7, 8]]
+    t, _ = finish_targets(tok[:, :1], 4, True, syn.COSINGLE)
+    assert t.tolist() == [[5, eos, -1, -1]]
+    ids = torch.tensor([[3, 4, 0, 0], [5, 6, 7, 8]])
+    assert torch.equal(set_eos_id(ids.clone(), 99, 0), orc.set_eos_id(ids.clone(), 99, 0))
+    assert set_eos_id(ids.clone(), 99, 0).tolist() == [[3, 4, 99, 0, 0], [5, 6, 7, 8, 99]]
+
+
+def test_t2s_packing_layout_and_config_recovery():
+    import numpy as np
+    from covomix_b200 import packing, synthetic as syn
+    for cfg in (syn.COSINGLE, syn.COMIX):
+        sd = syn.synthetic_t2s_state_dict(cfg, 3)
+        lightning = {"cfm_wrapper.model." + k: v for k, v in sd.items()}
+        assert packing.t2s_config_from_state_dict(lightning) == cfg
+        blob = packing.pack_t2s_weights(lightning, cfg)
+        assert bytes(blob[:8]) == b"COVOWTS1"
+        n = int(np.frombuffer(blob[8:12].tobytes(), dtype="<u4")[0])
+        assert n == 5 + 9 * cfg.source_depth + 1 + 13 * cfg.target_depth
+        fp32 = packing.pack_t2s_weights(sd, cfg, "fp32")
+        assert fp32.nbytes > blob.nbytes
+
+
+def test_dialogue_item_assembly():
+    from covomix_b200.pipeline import dialogue_item
+    it = dialogue_item(torch.arange(5), torch.arange(5) + 10, torch.ones(3, 160), torch.tensor([600, 2]), torch.tensor([7]))
+    assert it["phoneme_ids"].tolist() == [[0, 10], [1, 11], [2, 12], [501, 7], [2, 157]]
+    assert it["mask"].tolist() == [False, False, False, True, True]
+    assert it["cond"].shape == (5, 160) and float(it["cond"][3:].abs().sum()) == 0.0
+
+
+def test_accelerate_text2semantic_swaps_sample(monkeypatch):
+    import types
+    from covomix_b200 import dropin, synthetic as syn
+    import covomix_b200.t2s as t2s_mod
+
+    class FakeT2S:
+        def __init__(self, sd, cfg, device, weight_format="bf16"):
+            self.cfg = cfg
+
+        def sample(self, grapheme_token_ids, temperature=1., cond_scale=1., beam_search_decode=False, prompt_mel=None):
+            return torch.tensor([1, 2, 3])
+
+    monkeypatch.setattr(t2s_mod, "B200TextToSemantic", FakeT2S)
+    net = torch.nn.Module()
+    sd = syn.synthetic_t2s_state_dict(syn.COMIX, 3)
+    net.state_dict = lambda: sd
+    net.parameters = lambda: iter([torch.zeros(1)])
+    model = types.SimpleNamespace(cfm_wrapper=types.SimpleNamespace(model=net, sample=lambda **k: None))
+    dropin.accelerate_text2semantic(model, device="cuda:0")
+    assert model.cfm_wrapper._b200_t2s.cfg == syn.COMIX
+    assert model.cfm_wrapper.sample(grapheme_token_ids=torch.zeros(1, 4)).tolist() == [1, 2, 3]
