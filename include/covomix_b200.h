@@ -166,6 +166,26 @@ int covo_t2s_launches_per_generate(const covo_t2s* h);
 /* Bytes of decoder matrices one decoding step streams (the quantity the step is bound by). */
 size_t covo_t2s_weight_bytes_per_step(const covo_t2s* h);
 
+/* ---- prompt mel front-end -----------------------------------------------------------------------------------
+ * Replaces mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, center=False)
+ * (covomix/util/generate_mel.py:49-72), which extract_mel / prepare_oracle_hubert call on the acoustic prompt
+ * (monologue_generation.py:62-90) with the constants of monologue_generation.py:349-357. */
+typedef struct covo_mel_cfg {
+    int32_t n_fft;      /* 480 */
+    int32_t hop_size;   /* 160 */
+    int32_t win_size;   /* 480 (<= n_fft) */
+    int32_t num_mels;   /* 80 */
+} covo_mel_cfg;
+typedef struct covo_mel covo_mel;
+/* window: HOST f32 [win_size] (torch.hann_window); mel_basis: HOST f32 [num_mels, n_fft/2 + 1]
+ * (librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax); covomix_b200.frontend.slaney_mel_filterbank restates it). */
+int covo_mel_create(const covo_mel_cfg* cfg, const float* window, const float* mel_basis, int device, covo_mel** out);
+int covo_mel_destroy(covo_mel* h);
+/* Frames for L samples: (L + 2*pad - n_fft) / hop + 1 with pad = (n_fft - hop) / 2 (L >= pad + 1). */
+int covo_mel_frames(const covo_mel* h, int L);
+/* wav f32 [B, L] in [-1, 1] -> mel f32 [B, num_mels, frames(L)] = log(clamp(mel_basis @ |STFT|, 1e-5)). */
+int covo_mel_forward(covo_mel* h, const float* wav, float* mel, int B, int L, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------------ */
 const char* covo_last_error(void);
 int covo_version(void);

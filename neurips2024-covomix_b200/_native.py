@@ -23,6 +23,7 @@ EXPORTS = (
     "covo_version", "covo_dbg_gemm", "covo_dbg_attention", "covo_prof_begin", "covo_prof_end",
     "covo_t2s_create", "covo_t2s_destroy", "covo_t2s_workspace_bytes", "covo_t2s_generate",
     "covo_t2s_launches_per_generate", "covo_t2s_weight_bytes_per_step",
+    "covo_mel_create", "covo_mel_destroy", "covo_mel_frames", "covo_mel_forward",
 )
 
 
@@ -45,6 +46,10 @@ class T2SCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "dim", "source_depth", "target_depth", "heads", "dim_head", "num_text_token_ids", "num_semantic_token_ids",
         "two_output", "target_transformer_dim", "ff_mult", "text_pad_id", "weight_format")]
+
+
+class MelCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_fft", "hop_size", "win_size", "num_mels")]
 
 
 COVO_T2S_W_BF16, COVO_T2S_W_F32 = 0, 1
@@ -90,6 +95,10 @@ def lib() -> C.CDLL:
     L.covo_t2s_launches_per_generate.argtypes = [vp]
     L.covo_t2s_weight_bytes_per_step.argtypes = [vp]
     L.covo_t2s_weight_bytes_per_step.restype = sz
+    L.covo_mel_create.argtypes = [C.POINTER(MelCfg), vp, vp, i32, C.POINTER(vp)]
+    L.covo_mel_destroy.argtypes = [vp]
+    L.covo_mel_frames.argtypes = [vp, i32]
+    L.covo_mel_forward.argtypes = [vp, vp, vp, i32, i32, vp]
     L.covo_prof_begin.argtypes = []
     L.covo_prof_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), i32]
     for name in EXPORTS:

@@ -2,6 +2,7 @@
 #include "flow.cuh"
 #include "hifigan.cuh"
 #include "t2s.cuh"
+#include "frontend.cuh"
 
 using namespace covo;
 
@@ -405,6 +406,89 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
         fprintf(stderr, "[t2s trace] S9 logits=%lld barrier=%lld S10 sample=%lld barrier=%lld\n", tb[101] - tb[100],
                 tb[102] - tb[101], tb[103] - tb[102], tb[104] - tb[103]);
     }
+    return COVO_OK;
+}
+
+// ====================================================================================== mel front-end
+int covo_mel_create(const covo_mel_cfg* cfg, const float* window, const float* mel_basis, int device, covo_mel** out) {
+    if (!cfg || !window || !mel_basis || !out) return fail(COVO_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->n_fft < 2 || cfg->n_fft > 4096 || cfg->win_size < 1 || cfg->win_size > cfg->n_fft || cfg->hop_size < 1 ||
+        cfg->hop_size > cfg->n_fft || cfg->num_mels < 1)
+        return fail(COVO_ERR_INVALID, "unsupported mel config (n_fft=%d, hop=%d, win=%d, mels=%d)", cfg->n_fft, cfg->hop_size,
+                    cfg->win_size, cfg->num_mels);
+    DeviceGuard g(device);
+    covo_mel* h = new covo_mel();
+    h->cfg = *cfg;
+    h->n_freq = cfg->n_fft / 2 + 1;
+    int rc = check_device(device, &h->di);
+    if (rc == COVO_OK) {
+        std::vector<float2> tw(cfg->n_fft);
+        for (int j = 0; j < cfg->n_fft; ++j) {
+            const double ang = 2.0 * 3.14159265358979323846 * j / cfg->n_fft;
+            tw[j] = make_float2(static_cast<float>(cos(ang)), static_cast<float>(sin(ang)));
+        }
+        const size_t nb = static_cast<size_t>(cfg->num_mels) * h->n_freq * sizeof(float);
+        if (cudaMalloc(&h->window, cfg->win_size * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&h->twiddle, cfg->n_fft * sizeof(float2)) != cudaSuccess || cudaMalloc(&h->basis, nb) != cudaSuccess ||
+            cudaMemcpy(h->window, window, cfg->win_size * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h->twiddle, tw.data(), cfg->n_fft * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h->basis, mel_basis, nb, cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = fail(COVO_ERR_CUDA, "mel front-end: device allocation / copy failed");
+    }
+    if (rc != COVO_OK) {
+        covo_mel_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return COVO_OK;
+}
+
+int covo_mel_destroy(covo_mel* h) {
+    if (!h) return COVO_OK;
+    DeviceGuard g(h->di.device);
+    cudaDeviceSynchronize();
+    if (h->window) cudaFree(h->window);
+    if (h->twiddle) cudaFree(h->twiddle);
+    if (h->basis) cudaFree(h->basis);
+    delete h;
+    return COVO_OK;
+}
+
+int covo_mel_frames(const covo_mel* h, int L) {
+    if (!h) return 0;
+    const int pad = (h->cfg.n_fft - h->cfg.hop_size) / 2;
+    if (L < pad + 1 || L + 2 * pad < h->cfg.n_fft) return 0;
+    return (L + 2 * pad - h->cfg.n_fft) / h->cfg.hop_size + 1;
+}
+
+int covo_mel_forward(covo_mel* h, const float* wav, float* mel, int B, int L, void* stream) {
+    if (!h || !wav || !mel) return fail(COVO_ERR_INVALID, "null argument");
+    const int T = covo_mel_frames(h, L);
+    if (B < 1 || B > 65535 || T < 1) return fail(COVO_ERR_INVALID, "mel front-end: B=%d, L=%d gives no frame (reflect padding needs L > %d)", B, L,
+                                    (h->cfg.n_fft - h->cfg.hop_size) / 2);
+    DeviceGuard g(h->di.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MelArgs a;
+    a.wav = wav;
+    a.mel = mel;
+    a.window = h->window;
+    a.twiddle = h->twiddle;
+    a.basis = h->basis;
+    a.L = L;
+    a.T = T;
+    a.n_fft = h->cfg.n_fft;
+    a.hop = h->cfg.hop_size;
+    a.win = h->cfg.win_size;
+    a.n_freq = h->n_freq;
+    a.n_mels = h->cfg.num_mels;
+    a.pad = (h->cfg.n_fft - h->cfg.hop_size) / 2;
+    const size_t smem = sizeof(float) * (3 * static_cast<size_t>(a.n_fft) + a.n_freq);
+    if (smem > 48 * 1024)
+        COVO_CK(cudaFuncSetAttribute(mel_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ProfScope ps(PC_PROLOGUE, 0.0, st);
+    mel_frontend_kernel<<<dim3(T, B), 256, smem, st>>>(a);
+    COVO_CK(cudaGetLastError());
     return COVO_OK;
 }
 
