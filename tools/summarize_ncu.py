@@ -49,8 +49,10 @@ def full(path, out):
             tot = sum(st.values()) or 1
             f.write("- warp-stall samples: " + ", ".join(f"{k} {100*v/tot:.0f}%" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:7]) + "\n")
             try:
-                tr = float(d["dram__bytes_read.sum"].replace(",", "")) + float(d["dram__bytes_write.sum"].replace(",", ""))
-                f.write(f"- DRAM traffic = read + write = {tr:.1f} {units[hdr.index('dram__bytes_read.sum')]}\n")
+                scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6}
+                tr = sum(float(d[k].replace(",", "")) * scale[units[hdr.index(k)]]
+                         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                f.write(f"- DRAM traffic = read + write = {tr:.1f} Mbyte\n")
             except Exception:
                 pass
             f.write("\n")
