@@ -10,6 +10,7 @@ One "step" = one pass of the hot path over one batch of synthetic input:
         followed by the HiFi-GAN generator on the 8 x [80, 1500] generated mels -> 8 x 240032 samples.
     workload c2: VoSingle, 32 Euler steps, 10 s monologue (N = 650), B = 1, + vocoder.
     workload c4: the full pipeline per GPU (BASELINE.json configs[3]): CoMix text-to-semantic -> VoMix -> vocoder.
+    workload c4p: c4 software-pipelined over batches: T2S of the next batch on its own SM budget next to flow + vocoder.
     workload c5: HiFi-GAN sweep (one JSON line per point).
 value = B * 30 s * n_gpus / seconds-per-step (whole job, inputs resident in HBM).
 e2e   = the same through the public Python API with pinned HOST inputs and a device->host read of the waveform.
@@ -42,6 +43,11 @@ WORKLOADS = {
     # streams, EOS ignored: random-init weights would stop at a random position) -> VoMix (as C3) -> HiFi-GAN.
     "c4": dict(model="vomix", B=8, N=1650, prompt=150, method="euler", n_steps=64, t2s=dict(S=200, steps=1500),
                name="C4 (per GPU): CoMix T2S (1500 AR steps, 2 streams) -> VoMix 64 Euler steps -> HiFi-GAN, 30 s dialogues, batch 8"),
+    # same work, software-pipelined over batches on two streams with an SM budget per stage: the latency-bound T2S loop of
+    # batch i+1 (t2s_sms SMs) runs next to the flow sampler + vocoder of batch i (the remaining SMs)
+    "c4p": dict(model="vomix", B=8, N=1650, prompt=150, method="euler", n_steps=64, t2s=dict(S=200, steps=1500), t2s_sms=56,
+                name="C4 pipelined (per GPU): CoMix T2S of batch i+1 on 56 SMs || VoMix 64 Euler steps + HiFi-GAN of batch i "
+                     "on 92 SMs, 30 s dialogues, batch 8"),
 }
 
 
@@ -229,9 +235,12 @@ def run_b200(args):
     wl = WORKLOADS[args.workload]
     cfg, ids_h, cond_h, y0_h, mask_h = make_inputs(wl, seed=30 + rank)     # each rank = its own shard of utterances
     # weights: identical on every rank (seeded); rank 0 could equally broadcast them (NCCL) -- see DESIGN.md
+    n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    t2s_sms = int(os.environ.get("COVO_T2S_SMS", wl.get("t2s_sms", 0)))
+    flow_sms = n_sms - t2s_sms if t2s_sms else None
     sampler = B200FlowSampler(syn.synthetic_flow_state_dict(cfg, 1234), cfg, dev, torchdiffeq_ode_method=wl["method"],
-                              ode_step_size=1.0 / wl["n_steps"])
-    gen = B200Generator(syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234), syn.HIFIGAN_COVOMIX, dev)
+                              ode_step_size=1.0 / wl["n_steps"], sm_limit=flow_sms)
+    gen = B200Generator(syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234), syn.HIFIGAN_COVOMIX, dev, sm_limit=flow_sms)
     B, N, prompt = wl["B"], wl["N"], wl["prompt"]
     gen_frames = N - prompt
     audio_s_per_step = B * gen_frames / FRAME_RATE
@@ -242,7 +251,7 @@ def run_b200(args):
     t2s = text_d = text_p = None
     if "t2s" in wl:
         from covomix_b200.t2s import B200TextToSemantic
-        t2s = B200TextToSemantic(syn.synthetic_t2s_state_dict(syn.COMIX, 1234), syn.COMIX, dev)
+        t2s = B200TextToSemantic(syn.synthetic_t2s_state_dict(syn.COMIX, 1234), syn.COMIX, dev, sm_limit=t2s_sms or None)
         text_h = syn.synthetic_text_ids(syn.COMIX, B, wl["t2s"]["S"], seed=40 + rank, ragged=True)
         text_d, text_p = text_h.to(dev), text_h.pin_memory()
         assert wl["t2s"]["steps"] == gen_frames
@@ -255,6 +264,8 @@ def run_b200(args):
         return torch.cat((prompt_ids[:, :prompt], new), dim=1)
 
     def step_device():
+        if pipelined:
+            return step_pipe(text_d, ids_d, cond_d, y0_d)
         ids = semantic_ids(text_d, ids_d) if t2s is not None else ids_d
         mel = sampler.sample(phoneme_ids=ids, cond=cond_d, cond_scale=0.7, y0=y0_d)
         voc_in = mel[:, prompt:, :].permute(0, 2, 1)           # what the scripts do: sampled[:, mask].permute(0,2,1)
@@ -262,9 +273,37 @@ def run_b200(args):
 
     wav_host = torch.empty(B, 1, gen.out_len(gen_frames), dtype=torch.float32).pin_memory()
 
+    pipelined = bool(t2s_sms) and t2s is not None
+    if pipelined:
+        # Software pipeline over batches: the host first enqueues flow + vocoder of the CURRENT batch on stream B (CUDA-graph
+        # launches return at once), then runs the text-to-semantic loop of the NEXT batch on stream A (its one host sync is
+        # where the host waits), then joins B.  One step still consumes one batch of text and emits one batch of audio.
+        s_a, s_b = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        state = {"ids": semantic_ids(text_d, ids_d)}
+        torch.cuda.synchronize()
+
+        def step_pipe(text, prompt_ids, cond, y0):
+            cur = torch.cuda.current_stream()
+            s_a.wait_stream(cur)
+            s_b.wait_stream(cur)
+            with torch.cuda.stream(s_b):
+                mel = sampler.sample(phoneme_ids=state["ids"], cond=cond, cond_scale=0.7, y0=y0)
+                wav = gen(mel[:, prompt:, :].permute(0, 2, 1))
+            with torch.cuda.stream(s_a):
+                nxt = semantic_ids(text, prompt_ids)
+            cur.wait_stream(s_a)
+            cur.wait_stream(s_b)
+            state["ids"] = nxt
+            return wav
+
     def step_e2e():
         i = ids_p.to(dev, non_blocking=True)
         c = cond_p.to(dev, non_blocking=True)
+        if pipelined:
+            wav = step_pipe(text_p.to(dev, non_blocking=True), i, c, None)
+            wav_host.copy_(wav, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return wav_host
         if t2s is not None:
             i = semantic_ids(text_p.to(dev, non_blocking=True), i)
         mel = sampler.sample(phoneme_ids=i, cond=c, cond_scale=0.7)   # y0 = torch.randn_like on device, as the reference
@@ -328,6 +367,7 @@ def run_b200(args):
         # step bracketed by CUDA events on the launching stream), same workload, same process
         with nat.profile() as prof:
             step_device()
+        torch.cuda.synchronize()
         pr = prof.result
         total_kernel_ms = sum(v[0] for v in pr.values())
         g_ms, g_flops, g_n = pr["gemm_tc"]
@@ -375,7 +415,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 operands / f32 accumulate (flow), fp16 operands / f32 accumulate (vocoder)", "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B * world, "seq_len": N, "parallelism": f"utterance-sharded x{world}",
-                       "cond_scale": 0.7, "l2": "working set (0.8 GB weights + 1.2 GB activations) larger than L2; no flush needed"},
+                       "cond_scale": 0.7, "sm_budget": {"t2s": t2s_sms, "flow+vocoder": flow_sms} if t2s_sms else None, "l2": "working set (0.8 GB weights + 1.2 GB activations) larger than L2; no flush needed"},
             "clocks": clocks, "gpu_launches": launches * world,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},

@@ -186,6 +186,15 @@ int covo_mel_frames(const covo_mel* h, int L);
 /* wav f32 [B, L] in [-1, 1] -> mel f32 [B, num_mels, frames(L)] = log(clamp(mel_basis @ |STFT|, 1e-5)). */
 int covo_mel_forward(covo_mel* h, const float* wav, float* mel, int B, int L, void* stream);
 
+/* ---- SM budgets (stage overlap) ----------------------------------------------------------------------------------
+ * Every hot kernel is persistent (grid = min(work, SMs)).  Limiting a handle to n_sms lets two stages share the GPU on
+ * two streams without time-slicing each other -- e.g. the text-to-semantic loop of the next batch on 56 SMs
+ * next to the flow sampler of the current batch on the other 92 (bench.py --workload c4p).  Call before the first
+ * sample / forward / generate of the handle (plans built earlier keep their grids).  n_sms <= 0 restores the device count. */
+int covo_flow_set_sm_limit(covo_flow* h, int n_sms);
+int covo_hifigan_set_sm_limit(covo_hifigan* h, int n_sms);
+int covo_t2s_set_sm_limit(covo_t2s* h, int n_sms);
+
 /* ---- misc ------------------------------------------------------------------------------------------ */
 const char* covo_last_error(void);
 int covo_version(void);

@@ -24,6 +24,7 @@ EXPORTS = (
     "covo_t2s_create", "covo_t2s_destroy", "covo_t2s_workspace_bytes", "covo_t2s_generate",
     "covo_t2s_launches_per_generate", "covo_t2s_weight_bytes_per_step",
     "covo_mel_create", "covo_mel_destroy", "covo_mel_frames", "covo_mel_forward",
+    "covo_flow_set_sm_limit", "covo_hifigan_set_sm_limit", "covo_t2s_set_sm_limit",
 )
 
 
@@ -99,6 +100,8 @@ def lib() -> C.CDLL:
     L.covo_mel_destroy.argtypes = [vp]
     L.covo_mel_frames.argtypes = [vp, i32]
     L.covo_mel_forward.argtypes = [vp, vp, vp, i32, i32, vp]
+    for fn in (L.covo_flow_set_sm_limit, L.covo_hifigan_set_sm_limit, L.covo_t2s_set_sm_limit):
+        fn.argtypes = [vp, i32]
     L.covo_prof_begin.argtypes = []
     L.covo_prof_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), i32]
     for name in EXPORTS:

@@ -492,6 +492,19 @@ int covo_mel_forward(covo_mel* h, const float* wav, float* mel, int B, int L, vo
     return COVO_OK;
 }
 
+// ====================================================================================== SM budgets
+namespace {
+int apply_sm_limit(DeviceInfo* di, int n_sms) {
+    cudaDeviceProp p;
+    COVO_CK(cudaGetDeviceProperties(&p, di->device));
+    di->num_sms = (n_sms <= 0 || n_sms > p.multiProcessorCount) ? p.multiProcessorCount : n_sms;
+    return COVO_OK;
+}
+}  // namespace
+int covo_flow_set_sm_limit(covo_flow* h, int n_sms) { return h ? apply_sm_limit(&h->di, n_sms) : fail(COVO_ERR_INVALID, "null handle"); }
+int covo_hifigan_set_sm_limit(covo_hifigan* h, int n_sms) { return h ? apply_sm_limit(&h->di, n_sms) : fail(COVO_ERR_INVALID, "null handle"); }
+int covo_t2s_set_sm_limit(covo_t2s* h, int n_sms) { return h ? apply_sm_limit(&h->di, n_sms) : fail(COVO_ERR_INVALID, "null handle"); }
+
 // ====================================================================================== profiler
 int covo_prof_begin(void) {
     Profiler& p = prof();

@@ -23,7 +23,7 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 
 class B200FlowSampler:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[FlowConfig] = None, device="cuda:0",
-                 torchdiffeq_ode_method: str = "midpoint", ode_step_size: float = 0.0625):
+                 torchdiffeq_ode_method: str = "midpoint", ode_step_size: float = 0.0625, sm_limit: Optional[int] = None):
         self.cfg = cfg if cfg is not None else flow_config_from_state_dict(state_dict)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -39,6 +39,8 @@ class B200FlowSampler:
         L = nat.lib()
         nat.check(L.covo_flow_create(C.byref(ccfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
                                      self.device.index or 0, C.byref(self._h)), "covo_flow_create")
+        if sm_limit:       # persistent kernels of this handle use at most sm_limit SMs (stage overlap, see include/covomix_b200.h)
+            nat.check(L.covo_flow_set_sm_limit(self._h, int(sm_limit)), "covo_flow_set_sm_limit")
         self._ws: Dict[tuple, torch.Tensor] = {}
 
     # --------------------------------------------------------------------------------

@@ -62,7 +62,7 @@ def finish_targets(tokens: torch.Tensor, steps: int, stopped: bool, cfg: T2SConf
 
 class B200TextToSemantic:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[T2SConfig] = None, device="cuda:0",
-                 weight_format: str = "bf16"):
+                 weight_format: str = "bf16", sm_limit: Optional[int] = None):
         self.cfg = cfg if cfg is not None else t2s_config_from_state_dict(state_dict)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -79,6 +79,8 @@ class B200TextToSemantic:
         self._h = C.c_void_p()
         nat.check(nat.lib().covo_t2s_create(C.byref(ccfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
                                             self.device.index or 0, C.byref(self._h)), "covo_t2s_create")
+        if sm_limit:       # the decode kernel's grid: sm_limit CTAs instead of one per SM (stage overlap)
+            nat.check(nat.lib().covo_t2s_set_sm_limit(self._h, int(sm_limit)), "covo_t2s_set_sm_limit")
         self._ws: Dict[tuple, torch.Tensor] = {}
 
     def close(self):

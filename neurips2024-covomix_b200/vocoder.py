@@ -22,7 +22,7 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 
 class B200Generator:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: HifiganConfig = HIFIGAN_COVOMIX, device="cuda:0",
-                 h_format: str = "fp16"):
+                 h_format: str = "fp16", sm_limit=None):
         self.h = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -48,6 +48,8 @@ class B200Generator:
         self._h = C.c_void_p()
         nat.check(nat.lib().covo_hifigan_create(C.byref(ccfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
                                                 self.device.index or 0, C.byref(self._h)), "covo_hifigan_create")
+        if sm_limit:
+            nat.check(nat.lib().covo_hifigan_set_sm_limit(self._h, int(sm_limit)), "covo_hifigan_set_sm_limit")
         self._ws: Dict[tuple, torch.Tensor] = {}
 
     # reference-API no-ops (weights are already folded / on device)
