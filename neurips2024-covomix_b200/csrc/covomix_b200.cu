@@ -225,7 +225,7 @@ int covo_t2s_create(const covo_t2s_cfg* cfg, const void* packed_weights, size_t 
     if (cfg->dim_head != T2S_DH) return fail(COVO_ERR_INVALID, "dim_head=%d unsupported (64 only)", cfg->dim_head);
     if (cfg->target_depth < 1 || cfg->target_depth > T2S_MAX_DEPTH || cfg->source_depth < 0)
         return fail(COVO_ERR_INVALID, "target_depth=%d / source_depth=%d out of range", cfg->target_depth, cfg->source_depth);
-    if (cfg->dim % 8 || cfg->target_transformer_dim % 16 || cfg->heads < 1 || (cfg->num_semantic_token_ids + 1) % 2 ||
+    if (cfg->dim % 8 || cfg->target_transformer_dim % 64 || (cfg->heads * cfg->dim_head) % 64 || cfg->heads < 1 || (cfg->num_semantic_token_ids + 1) % 2 ||
         cfg->num_semantic_token_ids + 1 > T2S_THREADS)
         return fail(COVO_ERR_INVALID, "unsupported dims (dim=%d, target dim=%d, heads=%d, semantic ids=%d)", cfg->dim,
                     cfg->target_transformer_dim, cfg->heads, cfg->num_semantic_token_ids);
@@ -301,7 +301,8 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
     memset(&a, 0, sizeof(a));
     int trace_step = -1;
     const int H = c.heads, n_ctx = S + 1;
-    const size_t ctx_per = static_cast<size_t>(B) * H * n_ctx * T2S_DH, cache_per = static_cast<size_t>(B) * H * max_length * T2S_DH;
+    const int n_ctx_r = round_up(n_ctx, 32), max_len_r = round_up(max_length, 32);
+    const size_t ctx_per = static_cast<size_t>(B) * H * n_ctx_r * T2S_DH, cache_per = static_cast<size_t>(B) * H * max_len_r * T2S_DH;
     for (int L = 0; L < c.target_depth; ++L) {
         const T2SDecLayerW& d = h->dec[L];
         T2SLayerW& w = a.L[L];
@@ -333,6 +334,8 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
     a.n_logits = h->n_logits;
     a.n_ctx = n_ctx;
     a.max_len = max_length;
+    a.n_ctx_r = n_ctx_r;
+    a.max_len_r = max_len_r;
     a.topk = top_k;
     {
         const char* dm = getenv("COVO_T2S_DEBUG_SKIP");     // bit mask: 1 all work, 2 attention, 4 matrix products, 8 sampler, 16 no weight prefetch, 32 plain (not evict-first) weight loads

@@ -135,28 +135,39 @@ __global__ void t2s_geglu_kernel(const float* __restrict__ h, float* __restrict_
     g[i] = gelu_erf(h[m * 2 * fi + fi + j]) * h[m * 2 * fi + j];
 }
 
-// kv [B*S1, 2*inner] of the encoded text + null_kv [2,H,64] -> ctx k / v [B][H][1+S1][64] (null first, :253-257);
+// kv [B*S1, 2*inner] of the encoded text + null_kv [2,H,64] -> cross-attention context of one decoder layer (null first,
+// :253-257) in the layout the decode kernel reads (see T2SLayerW), n_alloc = n_ctx rounded up to 32;
 // cmask [B][1+S1] = 1 | source_mask (:259-260)
 __global__ void t2s_ctx_scatter_kernel(const float* __restrict__ kv, const float* __restrict__ null_kv,
-                                       const uint8_t* __restrict__ mask, float* __restrict__ ck, float* __restrict__ cv,
-                                       uint8_t* __restrict__ cmask, int B, int S1, int H) {
+                                       const uint8_t* __restrict__ mask, void* __restrict__ ck, void* __restrict__ cv,
+                                       uint8_t* __restrict__ cmask, int B, int S1, int H, int n_alloc, int kv16) {
     const int inner = H * T2S_DH, n_ctx = S1 + 1;
-    const size_t n = static_cast<size_t>(B) * H * n_ctx * T2S_DH;
+    const size_t n = static_cast<size_t>(B) * H * n_ctx * (T2S_DH / 2);
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int d = i % T2S_DH;
-    const int j = (i / T2S_DH) % n_ctx;
-    const int h = (i / (static_cast<size_t>(T2S_DH) * n_ctx)) % H;
-    const int b = i / (static_cast<size_t>(T2S_DH) * n_ctx * H);
+    const int dp = i % (T2S_DH / 2);                       // dim pair
+    const int j = (i / (T2S_DH / 2)) % n_ctx;
+    const int h = (i / (static_cast<size_t>(T2S_DH / 2) * n_ctx)) % H;
+    const int b = i / (static_cast<size_t>(T2S_DH / 2) * n_ctx * H);
+    float2 k2, v2;
     if (j == 0) {
-        ck[i] = null_kv[h * T2S_DH + d];
-        cv[i] = null_kv[(H + h) * T2S_DH + d];
+        k2 = *reinterpret_cast<const float2*>(null_kv + h * T2S_DH + 2 * dp);
+        v2 = *reinterpret_cast<const float2*>(null_kv + (H + h) * T2S_DH + 2 * dp);
     } else {
-        const float* r = kv + (static_cast<size_t>(b) * S1 + (j - 1)) * 2 * inner + h * T2S_DH + d;
-        ck[i] = r[0];
-        cv[i] = r[inner];
+        const float* r = kv + (static_cast<size_t>(b) * S1 + (j - 1)) * 2 * inner + h * T2S_DH + 2 * dp;
+        k2 = *reinterpret_cast<const float2*>(r);
+        v2 = *reinterpret_cast<const float2*>(r + inner);
     }
-    if (h == 0 && d == 0) cmask[b * n_ctx + j] = j == 0 ? 1 : mask[b * S1 + j - 1];
+    const size_t bh = static_cast<size_t>(b) * H + h;
+    if (kv16) {
+        const __nv_bfloat162 kp = __floats2bfloat162_rn(k2.x, k2.y), vp = __floats2bfloat162_rn(v2.x, v2.y);
+        static_cast<uint32_t*>(ck)[(bh * (n_alloc / 32) + j / 32) * 1024 + dp * 32 + (j & 31)] = *reinterpret_cast<const uint32_t*>(&kp);
+        static_cast<uint32_t*>(cv)[(bh * n_alloc + j) * 32 + dp] = *reinterpret_cast<const uint32_t*>(&vp);
+    } else {
+        *reinterpret_cast<float2*>(static_cast<float*>(ck) + (bh * n_alloc + j) * T2S_DH + 2 * dp) = k2;
+        *reinterpret_cast<float2*>(static_cast<float*>(cv) + (bh * n_alloc + j) * T2S_DH + 2 * dp) = v2;
+    }
+    if (h == 0 && dp == 0) cmask[b * n_ctx + j] = j == 0 ? 1 : mask[b * S1 + j - 1];
 }
 
 // ======================================================================================================================
@@ -176,15 +187,19 @@ struct T2SLayerW {
     const float* ff1_b;
     const void* ff2;         // [Dt, ffi_pad]
     const float* ff2_b;
-    const float* ctx_k;      // [B][H][n_ctx][64]
-    const float* ctx_v;
-    float* kcache;           // [B][H][max_len][64]  (rotated keys)
-    float* vcache;
+    // KV storage, per (b, h), n_alloc = positions rounded up to 32:
+    //   fp32 matrices : K, V fp32 [n_alloc][64]
+    //   bf16 matrices : K bf16x2 words, blocked-transposed [n_alloc/32][32 dim pairs][32 positions] (a lane owns a key and
+    //                   reads one coalesced word per dim pair); V bf16x2 words [n_alloc][32] (a lane owns two dims)
+    const void* ctx_k;       // cross-attention context (null kv first), n_alloc = n_ctx_r
+    const void* ctx_v;
+    void* kcache;            // self-attention cache (rotated keys), n_alloc = max_len_r
+    void* vcache;
 };
 
 struct T2SDecArgs {
     T2SLayerW L[T2S_MAX_DEPTH];
-    int depth, B, Dt, inner, H, ffi, ffi_pad, n_out, demb, n_logits, n_ctx, max_len, topk, ignore_eos, dbg_mode;
+    int depth, B, Dt, inner, H, ffi, ffi_pad, n_out, demb, n_logits, n_ctx, max_len, n_ctx_r, max_len_r, topk, ignore_eos, dbg_mode;
     float temperature;
     long long eos_id;
     const float* emb;            // [n_logits, demb] fp32: input embedding and (tied) logit projection
@@ -382,6 +397,146 @@ __device__ __forceinline__ void t2s_gemv_rows(const WT* __restrict__ W, int ldw,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core path for wide batches (bf16 matrices, NB >= 4).  With 8 rows of activations the CUDA-core product above is
+// bound by shared-memory reads and FMA issue (16 LDS.128 + 128 FMA per 16-byte weight load); a warp-level
+// mma.sync m16n8k16 takes the batch as its n = 8 dimension instead: A = 16 weight rows x 16 k (bf16, straight from global
+// memory), B = 16 k x 8 batch rows (bf16 activations in shared memory), D = 16 x 8 fp32.  (tcgen05 wants M >= 64 rows of
+// the *moving* operand per CTA and a TMEM round trip per stage; for a 16 x 8 x K product that is re-launched 26 times per
+// decoding step behind a grid barrier, the register-resident warp MMA is the right tool.)
+//  * k is permuted inside every 64-k block so that a lane's A fragments for four consecutive MMAs are two contiguous
+//    16-byte loads per row (lane c of a quad owns k [8c, 8c+8) and [32+8c, 32+8c+8)), and the activations are stored in the
+//    matching "MMA order" so that a quad reads 32 contiguous bytes per MMA (t2s_mma_pos);
+//  * a unit = 8 primary rows + 8 secondary rows (A rows 0-7 / 8-15), so a lane ends up with a (primary, secondary) pair for
+//    two batch rows -- exactly what the rotary / GEGLU / two-plain-rows epilogues of the CUDA-core path take;
+//  * the 16 warps of a CTA split K of ONE unit (one 64-k block each for K = 1024) and reduce their D fragments through
+//    shared memory: all loads of a unit are in flight at once, and a stage of few units still finishes in one round trip.
+__device__ __forceinline__ void t2s_mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// position (in elements) of physical k (multiple of 4) inside the MMA-ordered activation row
+__device__ __forceinline__ int t2s_mma_pos(int k) {
+    const int q = (k >> 2) & 15;                                  // 4-element group inside the 64-k block
+    const int c = (q & 7) >> 1, s = (q & 1) | ((q >> 3) << 1);    // owning lane of the quad, MMA index
+    return (k & ~63) + 16 * s + 4 * c;
+}
+
+template <int NB, class Pre, class Epi>
+__device__ __forceinline__ void t2s_gemv_mma(const __nv_bfloat16* __restrict__ W, int ldw, int n_units, int unit_rows,
+                                             int row_stride, int pair_off, int primary_limit, int K,
+                                             const __nv_bfloat16* sxb, int ldxb, float4* sfrag, Pre pre, Epi epi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int nblk = K / 64;
+    if (t2s_dbg_skip_gemv) n_units = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int r0 = u * unit_rows + g * row_stride;
+        const bool valid = r0 < primary_limit;
+        const int r0l = valid ? r0 : 0, r1 = r0 + pair_off;
+        float2 pf0 = make_float2(0.f, 0.f), pf1 = pf0;
+        if (warp == 0 && valid) {
+            if (2 * c < NB) pf0 = pre(r0, r1, 2 * c);
+            if (2 * c + 1 < NB) pf1 = pre(r0, r1, 2 * c + 1);
+        }
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int blk = warp; blk < nblk; blk += T2S_WARPS) {
+            const __nv_bfloat16* pa = W + static_cast<size_t>(r0l) * ldw + blk * 64 + 8 * c;
+            const __nv_bfloat16* pb = W + static_cast<size_t>(r0l + pair_off) * ldw + blk * 64 + 8 * c;
+            const uint4 p0 = t2s_ld_stream(pa), p1 = t2s_ld_stream(pa + 32);
+            const uint4 s0 = t2s_ld_stream(pb), s1 = t2s_ld_stream(pb + 32);
+            const uint2* xb = reinterpret_cast<const uint2*>(sxb + g * ldxb + blk * 64 + 4 * c);
+            const uint2 x0 = xb[0], x1 = xb[4], x2 = xb[8], x3 = xb[12];
+            t2s_mma_bf16(d, p0.x, s0.x, p0.y, s0.y, x0.x, x0.y);
+            t2s_mma_bf16(d, p0.z, s0.z, p0.w, s0.w, x1.x, x1.y);
+            t2s_mma_bf16(d, p1.x, s1.x, p1.y, s1.y, x2.x, x2.y);
+            t2s_mma_bf16(d, p1.z, s1.z, p1.w, s1.w, x3.x, x3.y);
+        }
+        sfrag[warp * 32 + lane] = make_float4(d[0], d[1], d[2], d[3]);
+        __syncthreads();
+        if (warp == 0) {
+            const int nw = nblk < T2S_WARPS ? nblk : T2S_WARPS;
+            float4 acc = sfrag[lane];
+            for (int w = 1; w < nw; ++w) {
+                const float4 v = sfrag[w * 32 + lane];
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+            }
+            if (valid) {
+                if (2 * c < NB) epi(r0, r1, 2 * c, acc.x, acc.z, pf0);
+                if (2 * c + 1 < NB) epi(r0, r1, 2 * c + 1, acc.y, acc.w, pf1);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// L2 prefetch of the rows of this CTA's units in the next tensor-core stage
+__device__ __forceinline__ void t2s_prefetch_team(const void* W, int row_bytes, int n_units, int unit_rows, int row_stride,
+                                                  int pair_off, int primary_limit) {
+    if (t2s_dbg_no_prefetch) return;
+    const char* base = static_cast<const char*>(W);
+    const int lines = (row_bytes + 127) / 128;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (int i = threadIdx.x; i < 16 * lines; i += T2S_THREADS) {
+            const int rr = i / lines, ln = i - rr * lines;
+            const int r0 = u * unit_rows + (rr & 7) * row_stride;
+            if (r0 >= primary_limit) continue;
+            const char* row = base + static_cast<size_t>(r0 + (rr >> 3) * pair_off) * row_bytes + ln * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+        }
+    }
+}
+
+// bf16 activations in MMA order: sxb[b][t2s_mma_pos(j)] = bf16(x[b][j] * gamma[j]) (gamma == nullptr: plain copy; sscale is
+// only written with gamma).  Rows NB..7 of sxb stay zero (cleared once at kernel start).  D % 64 == 0.
+template <int NB>
+__device__ __forceinline__ void t2s_load_bf16(const float* x, const float* __restrict__ gamma, int D, __nv_bfloat16* sxb,
+                                              int ldxb, float* sred, float* sscale) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float ss[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+    for (int j = tid * 4; j < D; j += T2S_THREADS * 4) {
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (gamma != nullptr) g = *reinterpret_cast<const float4*>(gamma + j);
+        float4 v[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b] = __ldcg(reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * D + j));
+        const int dst = t2s_mma_pos(j);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v[b].x * g.x, v[b].y * g.y);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(v[b].z * g.z, v[b].w * g.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(sxb + b * ldxb + dst) = pk;
+            ss[b] = fmaf(v[b].x, v[b].x, fmaf(v[b].y, v[b].y, fmaf(v[b].z, v[b].z, fmaf(v[b].w, v[b].w, ss[b]))));
+        }
+    }
+    if (gamma != nullptr) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
+            if (lane == 0) sred[b * T2S_WARPS + warp] = ss[b];
+        }
+    }
+    __syncthreads();
+    if (gamma != nullptr) {
+        if (tid < NB) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < T2S_WARPS; ++w) t += sred[tid * T2S_WARPS + w];
+            sscale[tid] = sqrtf(static_cast<float>(D)) / fmaxf(sqrtf(t), 1e-12f);
+        }
+        __syncthreads();
+    }
+}
+
 // Ask L2 for the weight rows this warp will use in the NEXT stage before waiting at the grid barrier: the rows do not
 // depend on the activations, so an HBM miss overlaps the barrier and the activation load.  (L1 would be the better target
 // but gpu-scope fences invalidate it.)
@@ -464,7 +619,8 @@ __device__ __forceinline__ void t2s_load_plain(const float* src, int n, int half
 // self attention at B = 8) the result goes straight to attn[b][h*64 ...]; otherwise the CTA writes a partial and the last CTA
 // to arrive for (b, h) merges the partials -- no extra grid barrier either way.  Masked keys score -FLT_MAX like the
 // reference's masked_fill (attend_t2s.py:151-153).
-__device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB, const float* Kc, const float* Vc, int n_alloc,
+template <bool KV16>
+__device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB, const void* Kc, const void* Vc, int n_alloc,
                                                     int nkeys, const uint8_t* mask, float* sq, float* spart, int* sflag, int trace_base) {
 #define T2S_AMARK(id)                                                                                  \
     do {                                                                                              \
@@ -474,11 +630,12 @@ __device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblocks = (nkeys + 31) / 32;
     const int BH = NB * a.H;
-    // blocks per group: the 16 warps of a CTA work in parallel, so a full group costs no more latency than one block and
-    // saves the cross-CTA merge; groups are only made smaller when that is needed to give every SM a unit
-    int bpg = nblocks < T2S_WARPS ? nblocks : T2S_WARPS;
-    while (bpg > 4 && BH * ((nblocks + bpg - 1) / bpg) * 2 <= static_cast<int>(gridDim.x) && nblocks > bpg) bpg >>= 1;
-    const int ngroups = (nblocks + bpg - 1) / bpg;                                              // <= T2S_MAXS
+    // groups: a CTA takes up to 16 blocks (one per warp; a full group costs no more latency than one block and, when it
+    // covers the whole sequence, saves the cross-CTA merge), or up to 32 (two per warp) when that lets all units run in
+    // one round of the grid
+    int ngroups = (nblocks + T2S_WARPS - 1) / T2S_WARPS;
+    if (BH * ngroups > static_cast<int>(gridDim.x)) ngroups = (nblocks + 2 * T2S_WARPS - 1) / (2 * T2S_WARPS);
+    const int bpg = (nblocks + ngroups - 1) / ngroups;                                           // <= 32
     const int units = BH * ngroups;
     constexpr float NEG = -3.402823466e38f;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -490,59 +647,97 @@ __device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB,
         }
         __syncthreads();
         T2S_AMARK(1);
-        const int kb = (g * bpg + warp) * 32;
         float m = NEG, l = 0.f;
         float2 o = make_float2(0.f, 0.f);
-        if (warp < bpg && kb < nkeys) {
-            const float* Kb = Kc + static_cast<size_t>(bh) * n_alloc * T2S_DH;
-            const float* Vb = Vc + static_cast<size_t>(bh) * n_alloc * T2S_DH;
+        for (int wb = warp; wb < bpg; wb += T2S_WARPS) {
+            const int kb = (g * bpg + wb) * 32;
+            if (kb >= nkeys) break;
             const int j = kb + lane;
             const int cnt = min(32, nkeys - kb);
             float sc = NEG;
-            if (j < nkeys) {
-                const float4* kr = reinterpret_cast<const float4*>(Kb + static_cast<size_t>(j) * T2S_DH);
-                float4 kv[T2S_DH / 4];
+            if constexpr (KV16) {
+                // a lane owns key kb + lane: one coalesced 4-byte word (two dims) per load, 32 loads
+                const uint32_t* Kw = static_cast<const uint32_t*>(Kc) + (static_cast<size_t>(bh) * (n_alloc / 32) + kb / 32) * 1024 + lane;
+                uint32_t kw[32];
 #pragma unroll
-                for (int d = 0; d < T2S_DH / 4; ++d) kv[d] = __ldcg(kr + d);
+                for (int d = 0; d < 32; ++d) kw[d] = __ldcg(Kw + d * 32);
                 float acc = 0.f;
 #pragma unroll
-                for (int d = 0; d < T2S_DH / 4; ++d) {
-                    const float4 qq = *reinterpret_cast<const float4*>(sq + 4 * d);
-                    acc = fmaf(qq.x, kv[d].x, acc);
-                    acc = fmaf(qq.y, kv[d].y, acc);
-                    acc = fmaf(qq.z, kv[d].z, acc);
-                    acc = fmaf(qq.w, kv[d].w, acc);
+                for (int d = 0; d < 32; ++d) {
+                    const float2 qq = *reinterpret_cast<const float2*>(sq + 2 * d);
+                    acc = fmaf(qq.x, __uint_as_float(kw[d] << 16), acc);
+                    acc = fmaf(qq.y, __uint_as_float(kw[d] & 0xffff0000u), acc);
                 }
-                sc = (mask != nullptr && !mask[b * a.n_ctx + j]) ? NEG : acc;
+                if (j < nkeys) sc = (mask != nullptr && !mask[b * a.n_ctx + j]) ? NEG : acc;
+            } else {
+                const float* Kb = static_cast<const float*>(Kc) + static_cast<size_t>(bh) * n_alloc * T2S_DH;
+                if (j < nkeys) {
+                    const float4* kr = reinterpret_cast<const float4*>(Kb + static_cast<size_t>(j) * T2S_DH);
+                    float4 kv[T2S_DH / 4];
+#pragma unroll
+                    for (int d = 0; d < T2S_DH / 4; ++d) kv[d] = __ldcg(kr + d);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int d = 0; d < T2S_DH / 4; ++d) {
+                        const float4 qq = *reinterpret_cast<const float4*>(sq + 4 * d);
+                        acc = fmaf(qq.x, kv[d].x, acc);
+                        acc = fmaf(qq.y, kv[d].y, acc);
+                        acc = fmaf(qq.z, kv[d].z, acc);
+                        acc = fmaf(qq.w, kv[d].w, acc);
+                    }
+                    sc = (mask != nullptr && !mask[b * a.n_ctx + j]) ? NEG : acc;
+                }
             }
             T2S_AMARK(2);
-            m = sc;
+            float mb = sc;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-            const float p = j < nkeys ? expf(sc - m) : 0.f;
-            l = p;
+            for (int off = 16; off > 0; off >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, off));
+            const float p = j < nkeys ? expf(sc - mb) : 0.f;
+            float lb = p;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+            for (int off = 16; off > 0; off >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, off);
             T2S_AMARK(3);
-            const float2* vr = reinterpret_cast<const float2*>(Vb + static_cast<size_t>(kb) * T2S_DH) + lane;
-            if (cnt == 32) {
-                float2 vv[32];
+            float2 ob = make_float2(0.f, 0.f);
+            if constexpr (KV16) {
+                const uint32_t* vr = static_cast<const uint32_t*>(Vc) + (static_cast<size_t>(bh) * n_alloc + kb) * 32 + lane;
+                uint32_t vw[32];
 #pragma unroll
-                for (int t = 0; t < 32; ++t) vv[t] = __ldcg(vr + t * (T2S_DH / 2));
+                for (int t = 0; t < 32; ++t) vw[t] = t < cnt ? __ldcg(vr + t * 32) : 0u;
 #pragma unroll
                 for (int t = 0; t < 32; ++t) {
                     const float pt = __shfl_sync(0xffffffffu, p, t);
-                    o.x = fmaf(pt, vv[t].x, o.x);
-                    o.y = fmaf(pt, vv[t].y, o.y);
+                    ob.x = fmaf(pt, __uint_as_float(vw[t] << 16), ob.x);
+                    ob.y = fmaf(pt, __uint_as_float(vw[t] & 0xffff0000u), ob.y);
                 }
             } else {
-                for (int t = 0; t < cnt; ++t) {
-                    const float2 vv = __ldcg(vr + t * (T2S_DH / 2));
-                    const float pt = __shfl_sync(0xffffffffu, p, t);
-                    o.x = fmaf(pt, vv.x, o.x);
-                    o.y = fmaf(pt, vv.y, o.y);
+                const float* Vb = static_cast<const float*>(Vc) + static_cast<size_t>(bh) * n_alloc * T2S_DH;
+                const float2* vr = reinterpret_cast<const float2*>(Vb + static_cast<size_t>(kb) * T2S_DH) + lane;
+                if (cnt == 32) {
+                    float2 vv[32];
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) vv[t] = __ldcg(vr + t * (T2S_DH / 2));
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        const float pt = __shfl_sync(0xffffffffu, p, t);
+                        ob.x = fmaf(pt, vv[t].x, ob.x);
+                        ob.y = fmaf(pt, vv[t].y, ob.y);
+                    }
+                } else {
+                    for (int t = 0; t < cnt; ++t) {
+                        const float2 vv = __ldcg(vr + t * (T2S_DH / 2));
+                        const float pt = __shfl_sync(0xffffffffu, p, t);
+                        ob.x = fmaf(pt, vv.x, ob.x);
+                        ob.y = fmaf(pt, vv.y, ob.y);
+                    }
                 }
             }
+            // online merge of this warp's blocks
+            const float mn = fmaxf(m, mb);
+            const float ra = l > 0.f ? expf(m - mn) : 0.f, rb = expf(mb - mn);
+            l = fmaf(l, ra, lb * rb);
+            o.x = fmaf(o.x, ra, ob.x * rb);
+            o.y = fmaf(o.y, ra, ob.y * rb);
+            m = mn;
         }
         T2S_AMARK(4);
         float* sp = spart + warp * T2S_PART;
@@ -552,7 +747,7 @@ __device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB,
         T2S_AMARK(5);
         // merge the warps' partials: thread d < 64 owns output dim d
         float Mg = NEG, Lg = 0.f, og = 0.f;
-        const int nw = min(bpg, nblocks - g * bpg);
+        const int nw = min(min(bpg, nblocks - g * bpg), T2S_WARPS);
         if (tid < T2S_DH) {
             for (int w = 0; w < nw; ++w) Mg = fmaxf(Mg, spart[w * T2S_PART]);
             for (int w = 0; w < nw; ++w) {
@@ -714,14 +909,20 @@ __device__ __forceinline__ void t2s_sample_unit(const T2SDecArgs& a, int s, int 
 
 template <class WT, int NB>
 __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid_constant__ T2SDecArgs a) {
+    constexpr bool kMMA = sizeof(WT) == 2;                 // bf16 matrices -> tensor-core path (mma.sync, batch = n dimension)
+    constexpr bool kKV16 = sizeof(WT) == 2;                // bf16 matrices -> bf16 KV cache / context (layouts above)
     extern __shared__ __align__(16) float smem[];
-    const int ldx = a.ffi_pad > a.Dt ? a.ffi_pad : a.Dt;
-    float* sx = smem;                                  // [NB][ldx]
-    float* spart = sx + NB * ldx;                      // [16 warps][66]  (also the sampler's 256-bin histogram)
-    float* sq = spart + T2S_WARPS * T2S_PART;          // [64]
+    const int kmax = a.ffi_pad > a.Dt ? a.ffi_pad : a.Dt;
+    const int ldx = kmax;                              // fp32 activation rows (CUDA-core path, and the logit stage)
+    const int ldxb = kmax + 16;                        // bf16 activation rows, 32 bytes past a multiple of 128 (conflict-free)
+    float* sx = smem;                                  // [NB][ldx] fp32  /  [8][ldxb] bf16 (same storage)
+    __nv_bfloat16* sxb = reinterpret_cast<__nv_bfloat16*>(smem);
+    float* spart = sx + (kMMA && 4 * ldxb > NB * ldx ? 4 * ldxb : NB * ldx);   // [16][32] float4: attention partials, sampler histogram, MMA fragments
+    float* sq = spart + T2S_WARPS * 32 * 4;            // [64]
     float* sred = sq + T2S_DH;                         // [NB * 16]
     float* sscale = sred + NB * T2S_WARPS;             // [8]
     int* sidx = reinterpret_cast<int*>(sscale + 8);    // [2 + 16]
+    float4* sfrag = reinterpret_cast<float4*>(spart);
     unsigned epoch = 0;
     const int tid = threadIdx.x;
     const int Dt = a.Dt, inner = a.inner;
@@ -730,6 +931,41 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
     const auto no_pre1 = [](int, int) { return 0.f; };
     const auto resid = [=](int r, int b) { return __ldcg(x + b * Dt + r); };
 
+    // activation staging for a projection with K inputs: RMSNorm'ed (gamma != nullptr) or plain
+    auto stage_in = [&](const float* src, const float* gamma, int K) {
+        if constexpr (kMMA) {
+            t2s_load_bf16<NB>(src, gamma, K, sxb, ldxb, sred, sscale);
+        } else {
+            if (gamma != nullptr) t2s_load_norm<NB>(src, gamma, K, t2s_half<WT>(K), sx, ldx, sred, sscale);
+            else t2s_load_plain<NB>(src, K, t2s_half<WT>(K), sx, ldx);
+        }
+    };
+    // a plain projection: n_rows rows of W [n_rows, K]; epi1(r, b, v, prefetched), pre1(r, b)
+    auto proj_rows = [&](const void* W, int n_rows, int K, auto pre1, auto epi1) {
+        if constexpr (kMMA) {
+            t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(W), K, n_rows / 16, 16, 1, 8, n_rows, K, sxb, ldxb, sfrag,
+                             [=](int r0, int r1, int b) { return make_float2(pre1(r0, b), pre1(r1, b)); },
+                             [=](int r0, int r1, int b, float v0, float v1, float2 pf) {
+                                 epi1(r0, b, v0, pf.x);
+                                 epi1(r1, b, v1, pf.y);
+                             });
+        } else {
+            t2s_gemv_rows<WT, NB>(static_cast<const WT*>(W), K, n_rows, K, sx, ldx, pre1, epi1);
+        }
+    };
+    auto prefetch_rows_plain = [&](const void* W, int K, int n_rows) {
+        if constexpr (kMMA) t2s_prefetch_team(W, K * 2, n_rows / 16, 16, 1, 8, n_rows);
+        else t2s_prefetch_plain<WT, NB>(W, K, n_rows);
+    };
+    auto prefetch_qkv = [&](const void* W) {
+        if constexpr (kMMA) t2s_prefetch_team(W, Dt * 2, 3 * inner / 16, 16, 2, 1, 3 * inner);
+        else t2s_prefetch_rows(W, Dt * static_cast<int>(sizeof(WT)), 3 * inner / 2, 2, 1, 2);
+    };
+
+    if constexpr (kMMA) {      // batch rows NB..7 of the MMA's n dimension: zero, never written again
+        for (int i = tid; i < 8 * ldxb / 2; i += T2S_THREADS) reinterpret_cast<uint32_t*>(sxb)[i] = 0u;
+        __syncthreads();
+    }
     // position 0 input: the start token (text2semantic.py:746-751)
     for (int i = blockIdx.x * T2S_THREADS + tid; i < NB * Dt; i += gridDim.x * T2S_THREADS) a.x[i] = a.start[i % Dt];
     if (t2s_grid_barrier(a, epoch)) return;
@@ -742,109 +978,122 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
             T2S_MARK(mk + 0);
             // ---- S1: self-attention q | k | v of the new position; rotary at position `step`; k, v appended to the cache
             if (work) {
-                t2s_load_norm<NB>(a.x, w.sa_gamma, Dt, t2s_half<WT>(Dt), sx, ldx, sred, sscale);
+                stage_in(a.x, w.sa_gamma, Dt);
                 T2S_MARK(mk + 1);
                 const float2* rope = a.rope + static_cast<size_t>(step) * (T2S_DH / 2);
-                const int H = a.H, max_len = a.max_len;
+                const int H = a.H;
                 float* qb = a.q;
-                float* kc = w.kcache;
-                float* vc = w.vcache;
-                t2s_gemv<WT, NB, 2>(static_cast<const WT*>(w.sa_qkv), Dt, 3 * inner / 2, 2, 1, Dt, sx, ldx, no_pre,
-                                    [=](int r0, int, int b, float v0, float v1, float2) {
-                                        const int sect = r0 / inner, c = r0 % inner, h = c / T2S_DH, d = c % T2S_DH;
-                                        v0 *= sscale[b];
-                                        v1 *= sscale[b];
-                                        if (sect < 2) {
-                                            const float2 cs = rope[d >> 1];
-                                            const float t0 = v0 * cs.x - v1 * cs.y;
-                                            v1 = v1 * cs.x + v0 * cs.y;
-                                            v0 = t0;
-                                        }
-                                        if (sect == 0) {
-                                            *reinterpret_cast<float2*>(qb + b * inner + c) = make_float2(v0, v1);
-                                        } else {
-                                            float* dst = (sect == 1 ? kc : vc) +
-                                                         ((static_cast<size_t>(b) * H + h) * max_len + step) * T2S_DH + d;
-                                            *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
-                                        }
-                                    });
-                t2s_prefetch_plain<WT, NB>(w.sa_out, inner, Dt);
+                void* kc = w.kcache;
+                void* vc = w.vcache;
+                const int max_len_r = a.max_len_r;
+                const auto epi = [=](int r0, int, int b, float v0, float v1, float2) {
+                    const int sect = r0 / inner, c = r0 % inner, h = c / T2S_DH, d = c % T2S_DH;
+                    v0 *= sscale[b];
+                    v1 *= sscale[b];
+                    if (sect < 2) {
+                        const float2 cs = rope[d >> 1];
+                        const float t0 = v0 * cs.x - v1 * cs.y;
+                        v1 = v1 * cs.x + v0 * cs.y;
+                        v0 = t0;
+                    }
+                    const size_t bh = static_cast<size_t>(b) * H + h;
+                    if (sect == 0) {
+                        *reinterpret_cast<float2*>(qb + b * inner + c) = make_float2(v0, v1);
+                    } else if constexpr (kKV16) {
+                        const __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+                        const uint32_t word = *reinterpret_cast<const uint32_t*>(&pk);
+                        if (sect == 1)      // blocked-transposed keys: [block of 32 positions][dim pair][position in block]
+                            static_cast<uint32_t*>(kc)[(bh * (max_len_r / 32) + step / 32) * 1024 + (d >> 1) * 32 + (step & 31)] = word;
+                        else
+                            static_cast<uint32_t*>(vc)[(bh * max_len_r + step) * 32 + (d >> 1)] = word;
+                    } else {
+                        float* dst = static_cast<float*>(sect == 1 ? kc : vc) + (bh * max_len_r + step) * T2S_DH + d;
+                        *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                    }
+                };
+                if constexpr (kMMA)
+                    t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(w.sa_qkv), Dt, 3 * inner / 16, 16, 2, 1, 3 * inner, Dt, sxb,
+                                     ldxb, sfrag, no_pre, epi);
+                else
+                    t2s_gemv<WT, NB, 2>(static_cast<const WT*>(w.sa_qkv), Dt, 3 * inner / 2, 2, 1, Dt, sx, ldx, no_pre, epi);
+                prefetch_rows_plain(w.sa_out, inner, Dt);
             }
             T2S_MARK(mk + 2);
             if (t2s_grid_barrier(a, epoch)) return;
             T2S_MARK(mk + 3);
             // ---- S2: causal self-attention of the one query over the step + 1 cached keys
             if (work && !(a.dbg_mode & 2))
-                t2s_attention_stage(a, NB, w.kcache, w.vcache, a.max_len, step + 1, nullptr, sq, spart, sidx,
+                t2s_attention_stage<kKV16>(a, NB, w.kcache, w.vcache, a.max_len_r, step + 1, nullptr, sq, spart, sidx,
                                     (L == 0 && step == t2s_trace_step) ? 106 : -1);
             T2S_MARK(mk + 4);
             if (t2s_grid_barrier(a, epoch)) return;
             T2S_MARK(mk + 5);
             // ---- S3: to_out + residual
             if (work) {
-                t2s_load_plain<NB>(a.attn, inner, t2s_half<WT>(inner), sx, ldx);
+                stage_in(a.attn, nullptr, inner);
                 T2S_MARK(mk + 6);
-                t2s_gemv_rows<WT, NB>(static_cast<const WT*>(w.sa_out), inner, Dt, inner, sx, ldx, resid,
-                                      [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
-                t2s_prefetch_plain<WT, NB>(w.ca_q, Dt, inner);
+                proj_rows(w.sa_out, Dt, inner, resid, [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
+                prefetch_rows_plain(w.ca_q, Dt, inner);
             }
             T2S_MARK(mk + 7);
             if (t2s_grid_barrier(a, epoch)) return;
             T2S_MARK(mk + 8);
             // ---- S4: cross-attention query
             if (work) {
-                t2s_load_norm<NB>(a.x, w.ca_gamma, Dt, t2s_half<WT>(Dt), sx, ldx, sred, sscale);
+                stage_in(a.x, w.ca_gamma, Dt);
                 float* qb = a.q;
-                t2s_gemv_rows<WT, NB>(static_cast<const WT*>(w.ca_q), Dt, inner, Dt, sx, ldx, no_pre1,
-                                      [=](int r, int b, float v, float) { qb[b * inner + r] = v * sscale[b]; });
-                t2s_prefetch_plain<WT, NB>(w.ca_out, inner, Dt);
+                proj_rows(w.ca_q, inner, Dt, no_pre1, [=](int r, int b, float v, float) { qb[b * inner + r] = v * sscale[b]; });
+                prefetch_rows_plain(w.ca_out, inner, Dt);
             }
             T2S_MARK(mk + 9);
             if (t2s_grid_barrier(a, epoch)) return;
             T2S_MARK(mk + 10);
             // ---- S5: cross attention over [null kv | encoded text] with the source padding mask
             if (work && !(a.dbg_mode & 2))
-                t2s_attention_stage(a, NB, w.ctx_k, w.ctx_v, a.n_ctx, a.n_ctx, a.ctx_mask, sq, spart, sidx,
+                t2s_attention_stage<kKV16>(a, NB, w.ctx_k, w.ctx_v, a.n_ctx_r, a.n_ctx, a.ctx_mask, sq, spart, sidx,
                                     (L == 0 && step == t2s_trace_step) ? 116 : -1);
             T2S_MARK(mk + 11);
             if (t2s_grid_barrier(a, epoch)) return;
             T2S_MARK(mk + 12);
             // ---- S6: to_out + residual
             if (work) {
-                t2s_load_plain<NB>(a.attn, inner, t2s_half<WT>(inner), sx, ldx);
-                t2s_gemv_rows<WT, NB>(static_cast<const WT*>(w.ca_out), inner, Dt, inner, sx, ldx, resid,
-                                      [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
-                t2s_prefetch_rows(w.ff1, Dt * static_cast<int>(sizeof(WT)), a.ffi, 1, a.ffi, 2);
+                stage_in(a.attn, nullptr, inner);
+                proj_rows(w.ca_out, Dt, inner, resid, [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
+                if constexpr (kMMA) t2s_prefetch_team(w.ff1, Dt * 2, (a.ffi + 7) / 8, 8, 1, a.ffi, a.ffi);
+                else t2s_prefetch_rows(w.ff1, Dt * static_cast<int>(sizeof(WT)), a.ffi, 1, a.ffi, 2);
             }
             T2S_MARK(mk + 13);
             if (t2s_grid_barrier(a, epoch)) return;
             T2S_MARK(mk + 14);
             // ---- S7: FF in-projection + GEGLU: row i (x part) is paired with row ffi + i (gate)
             if (work) {
-                t2s_load_norm<NB>(a.x, w.ff_gamma, Dt, t2s_half<WT>(Dt), sx, ldx, sred, sscale);
+                stage_in(a.x, w.ff_gamma, Dt);
                 T2S_MARK(mk + 15);
                 float* hb = a.hbuf;
                 const float* b1 = w.ff1_b;
                 const int ffi_pad = a.ffi_pad;
-                t2s_gemv<WT, NB, 2>(static_cast<const WT*>(w.ff1), Dt, a.ffi, 1, a.ffi, Dt, sx, ldx,
-                                    [=](int r0, int r1, int) { return make_float2(b1[r0], b1[r1]); },
-                                    [=](int r0, int, int b, float v0, float v1, float2 pf) {
-                                        hb[b * ffi_pad + r0] = gelu_erf(fmaf(v1, sscale[b], pf.y)) * fmaf(v0, sscale[b], pf.x);
-                                    });
-                t2s_prefetch_plain<WT, NB>(w.ff2, ffi_pad, Dt);
+                const auto pre = [=](int r0, int r1, int) { return make_float2(b1[r0], b1[r1]); };
+                const auto epi = [=](int r0, int, int b, float v0, float v1, float2 pf) {
+                    hb[b * ffi_pad + r0] = gelu_erf(fmaf(v1, sscale[b], pf.y)) * fmaf(v0, sscale[b], pf.x);
+                };
+                if constexpr (kMMA)
+                    t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(w.ff1), Dt, (a.ffi + 7) / 8, 8, 1, a.ffi, a.ffi, Dt, sxb, ldxb,
+                                     sfrag, pre, epi);
+                else
+                    t2s_gemv<WT, NB, 2>(static_cast<const WT*>(w.ff1), Dt, a.ffi, 1, a.ffi, Dt, sx, ldx, pre, epi);
+                prefetch_rows_plain(w.ff2, ffi_pad, Dt);
             }
             T2S_MARK(mk + 16);
             if (t2s_grid_barrier(a, epoch)) return;
             T2S_MARK(mk + 17);
             // ---- S8: FF out-projection + bias + residual
             if (work) {
-                t2s_load_plain<NB>(a.hbuf, a.ffi_pad, t2s_half<WT>(a.ffi_pad), sx, ldx);
+                stage_in(a.hbuf, nullptr, a.ffi_pad);
                 T2S_MARK(mk + 18);
                 const float* b2 = w.ff2_b;
-                t2s_gemv_rows<WT, NB>(static_cast<const WT*>(w.ff2), a.ffi_pad, Dt, a.ffi_pad, sx, ldx,
-                                      [=](int r, int b) { return __ldcg(x + b * Dt + r) + b2[r]; },
-                                      [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
-                if (L + 1 < a.depth) t2s_prefetch_rows(a.L[L + 1].sa_qkv, Dt * static_cast<int>(sizeof(WT)), 3 * inner / 2, 2, 1, 2);
+                proj_rows(w.ff2, Dt, a.ffi_pad, [=](int r, int b) { return __ldcg(x + b * Dt + r) + b2[r]; },
+                          [=](int r, int b, float v, float res) { x[b * Dt + r] = v + res; });
+                if (L + 1 < a.depth) prefetch_qkv(a.L[L + 1].sa_qkv);
                 else t2s_prefetch_plain<float, NB>(a.emb, a.demb, a.n_logits);
             }
             T2S_MARK(mk + 19);
@@ -852,7 +1101,7 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
             T2S_MARK(mk + 20);
         }
         T2S_MARK(100);
-        // ---- S9: final norm + tied logit projection per output stream (text2semantic.py:762-776), fp32 table
+        // ---- S9: final norm + tied logit projection per output stream (text2semantic.py:762-776), fp32 table, fp32 activations
         if ((a.dbg_mode & 1) == 0) {
             t2s_load_norm<NB>(a.x, a.final_gamma, Dt, 0, sx, ldx, sred, sscale);
             for (int s = 0; s < a.n_out; ++s) {
@@ -861,7 +1110,12 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
                 t2s_gemv_rows<float, NB>(a.emb, a.demb, a.n_logits, a.demb, sx + s * a.demb, ldx, no_pre1,
                                          [=](int r, int b, float v, float) { lg[b * n + r] = v * sscale[b]; });
             }
-            t2s_prefetch_rows(a.L[0].sa_qkv, Dt * static_cast<int>(sizeof(WT)), 3 * inner / 2, 2, 1, 2);
+            prefetch_qkv(a.L[0].sa_qkv);
+            if constexpr (kMMA) {      // the fp32 logit stage used rows NB..7's storage: clear it again for the MMA path
+                __syncthreads();
+                for (int i = tid; i < 8 * ldxb / 2; i += T2S_THREADS) reinterpret_cast<uint32_t*>(sxb)[i] = 0u;
+                __syncthreads();
+            }
         }
         T2S_MARK(101);
         if (t2s_grid_barrier(a, epoch)) return;
@@ -919,7 +1173,7 @@ inline int t2s_bind_weights(covo_t2s* h) {
     h->inner = c.heads * c.dim_head;
     h->fi_enc = static_cast<int>(c.dim * c.ff_mult * 2 / 3);
     h->ffi = static_cast<int>(c.target_transformer_dim * c.ff_mult * 2 / 3);
-    h->ffi_pad = round_up(h->ffi, 8);
+    h->ffi_pad = round_up(h->ffi, 64);      // K of the FF out-projection: whole 64-k blocks (tensor-core path)
     h->n_out = c.two_output ? 2 : 1;
     h->demb = c.target_transformer_dim / h->n_out;
     h->n_logits = c.num_semantic_token_ids + 1;
@@ -974,8 +1228,11 @@ inline int t2s_bind_weights(covo_t2s* h) {
 inline int t2s_pad_batch(int B) { return B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8)); }
 
 inline size_t t2s_decode_smem(const covo_t2s* h, int NB) {
-    const int ldx = h->ffi_pad > h->cfg.target_transformer_dim ? h->ffi_pad : h->cfg.target_transformer_dim;
-    return sizeof(float) * (static_cast<size_t>(NB) * ldx + T2S_WARPS * T2S_PART + T2S_DH + NB * T2S_WARPS + 8 + 2 + T2S_WARPS + 2);
+    const int kmax = h->ffi_pad > h->cfg.target_transformer_dim ? h->ffi_pad : h->cfg.target_transformer_dim;
+    size_t act = sizeof(float) * static_cast<size_t>(NB) * kmax;                  // fp32 rows
+    const size_t act16 = 2 * static_cast<size_t>(8) * (kmax + 16);                // 8 bf16 rows (tensor-core path)
+    if (act16 > act) act = act16;
+    return act + sizeof(float) * (T2S_WARPS * 32 * 4 + T2S_DH + NB * T2S_WARPS + 8 + 2 + T2S_WARPS + 2);
 }
 
 // Workspace layout for (B rows padded to NB, S1 text positions incl. EOS, max_len decode positions)
@@ -1011,8 +1268,8 @@ inline size_t t2s_layout(const covo_t2s* h, int NB, int S1, int max_len, void* w
     t.ge = a.take<float>(M * h->fi_enc);
     t.tmp = a.take<float>(M * c.dim);
     t.rope = a.take<float2>(static_cast<size_t>(rope_n) * (T2S_DH / 2));
-    const size_t ctx_n = static_cast<size_t>(c.target_depth) * NB * H * n_ctx * T2S_DH;
-    const size_t cache_n = static_cast<size_t>(c.target_depth) * NB * H * max_len * T2S_DH;
+    const size_t ctx_n = static_cast<size_t>(c.target_depth) * NB * H * round_up(n_ctx, 32) * T2S_DH;      // fp32-sized: covers both layouts
+    const size_t cache_n = static_cast<size_t>(c.target_depth) * NB * H * round_up(max_len, 32) * T2S_DH;
     t.ctx_k = a.take<float>(ctx_n);
     t.ctx_v = a.take<float>(ctx_n);
     t.kcache = a.take<float>(cache_n);
@@ -1079,13 +1336,15 @@ inline int t2s_enqueue_source(const covo_t2s* h, const T2SBuffers& t, int NB, in
         t2s_add_kernel<<<ceil_div(M * D, 256), 256, 0, st>>>(t.xe, t.tmp, static_cast<size_t>(M) * D);
     }
     t2s_rmsnorm_kernel<<<ceil_div(M, 8), 256, 0, st>>>(t.xe, h->enc_final.as<float>(), t.he, M, D);   // he = source_emb
-    const int n_ctx = S1 + 1;
-    const size_t per_layer = static_cast<size_t>(NB) * H * n_ctx * T2S_DH;
+    const int n_ctx = S1 + 1, n_ctx_r = round_up(n_ctx, 32);
+    const size_t per_layer = static_cast<size_t>(NB) * H * n_ctx_r * T2S_DH;
+    const int n_scatter = NB * H * n_ctx * (T2S_DH / 2);
     for (int L = 0; L < c.target_depth; ++L) {
         const T2SDecLayerW& d = h->dec[L];
         COVO_TRY(t2s_sgemm(t.he, d.ca_kv.as<float>(), nullptr, t.kve, M, 2 * inner, D, st));
-        t2s_ctx_scatter_kernel<<<ceil_div(static_cast<int>(per_layer), 256), 256, 0, st>>>(
-            t.kve, d.ca_null.as<float>(), t.mask, t.ctx_k + L * per_layer, t.ctx_v + L * per_layer, t.cmask, NB, S1, H);
+        t2s_ctx_scatter_kernel<<<ceil_div(n_scatter, 256), 256, 0, st>>>(t.kve, d.ca_null.as<float>(), t.mask, t.ctx_k + L * per_layer,
+                                                                       t.ctx_v + L * per_layer, t.cmask, NB, S1, H, n_ctx_r,
+                                                                       h->wdt == DT_BF16 ? 1 : 0);
     }
     COVO_CK(cudaGetLastError());
     return COVO_OK;

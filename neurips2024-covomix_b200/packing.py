@@ -271,7 +271,7 @@ def pack_t2s_weights(sd: Dict[str, torch.Tensor], cfg: T2SConfig, weight_format:
     b.add("dec.start", sd["start_token.speech"], DT_F32)
     b.add("dec.final.gamma", sd["target_transformer.final_norm.gamma"], DT_F32)
     fi = cfg.ff_inner(cfg.target_transformer_dim)
-    fip = _round_up(fi, 8)
+    fip = _round_up(fi, 64)          # whole 64-k blocks for the tensor-core path of the decode kernel
     for L in range(cfg.target_depth):
         p, q = f"target_transformer.layers.{L}.", f"dec.L{L}."
         b.add(q + "sa.gamma", sd[p + "0.norm.gamma"], DT_F32)
