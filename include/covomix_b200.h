@@ -188,8 +188,8 @@ int covo_mel_forward(covo_mel* h, const float* wav, float* mel, int B, int L, vo
 
 /* ---- SM budgets (stage overlap) ----------------------------------------------------------------------------------
  * Every hot kernel is persistent (grid = min(work, SMs)).  Limiting a handle to n_sms lets two stages share the GPU on
- * two streams without time-slicing each other -- e.g. the text-to-semantic loop of the next batch on 36 SMs
- * next to the flow sampler of the current batch on the other 112 (bench.py --workload c4p).  Call before the first
+ * two streams without time-slicing each other -- e.g. the text-to-semantic loop of the next batch on 28 SMs
+ * next to the flow sampler of the current batch on the other 120 (bench.py --workload c4p).  Call before the first
  * sample / forward / generate of the handle (plans built earlier keep their grids).  n_sms <= 0 restores the device count. */
 int covo_flow_set_sm_limit(covo_flow* h, int n_sms);
 int covo_hifigan_set_sm_limit(covo_hifigan* h, int n_sms);

@@ -7,11 +7,11 @@
 //    decoding step together, separated by grid barriers, and loop over steps without returning to the host -- no kernel
 //    launch, no host round trip and no re-read of the prefix per token (the reference re-embeds the whole prefix,
 //    re-projects the cross-attention context and launches ~200 kernels per step).  A step is a chain of skinny
-//    matrix-vector products (B <= 8 rows): it is bound by streaming the decoder weights (46 M parameters, 92 MB as bf16,
-//    resident in the 126 MB L2 after the first step) and by the barrier latency, not by the tensor cores, so the stages are
-//    CUDA-core GEMVs with 16-byte weight loads, fp32 activations in shared memory and fp32 accumulation.
-//    The sampler (top-k filter + Gumbel arg-max, text2semantic.py:104-132) and the EOS logic (:804-826) are stages of
-//    the same kernel.
+//    products (B <= 8 rows against 46 M parameters, 93 MB as bf16) bound by the latency of its 34 dependent stages, not
+//    by FLOPs or bytes: with bf16 matrices the products run on warp-level tensor cores (mma.sync, batch = n dimension,
+//    K split over the warps of a CTA; t2s_gemv_mma), with fp32 matrices on CUDA cores (t2s_gemv); fp32 accumulation,
+//    norms, softmax and logits either way.  Single-query attention over a bf16 (or fp32) KV cache, the sampler
+//    (top-k filter + Gumbel arg-max, text2semantic.py:104-132) and the EOS logic (:804-826) are stages of the same kernel.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -425,52 +425,79 @@ __device__ __forceinline__ int t2s_mma_pos(int k) {
     return (k & ~63) + 16 * s + 4 * c;
 }
 
-template <int NB, class Pre, class Epi>
-__device__ __forceinline__ void t2s_gemv_mma(const __nv_bfloat16* __restrict__ W, int ldw, int n_units, int unit_rows,
-                                             int row_stride, int pair_off, int primary_limit, int K,
-                                             const __nv_bfloat16* sxb, int ldxb, float4* sfrag, Pre pre, Epi epi) {
+template <int NB, int U, class Pre, class Epi>
+__device__ __forceinline__ void t2s_gemv_mma_u(const __nv_bfloat16* __restrict__ W, int ldw, int n_units, int unit_rows,
+                                               int row_stride, int pair_off, int primary_limit, int K,
+                                               const __nv_bfloat16* sxb, int ldxb, float4* sfrag, Pre pre, Epi epi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, c = lane & 3;
     const int nblk = K / 64;
-    if (t2s_dbg_skip_gemv) n_units = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int r0 = u * unit_rows + g * row_stride;
-        const bool valid = r0 < primary_limit;
-        const int r0l = valid ? r0 : 0, r1 = r0 + pair_off;
+    const int nw = nblk < T2S_WARPS ? nblk : T2S_WARPS;
+    // a CTA takes U units per round: U x 4 weight loads per lane in flight, and warps 0..U-1 reduce one unit each
+    for (int u0 = blockIdx.x * U; u0 < n_units; u0 += gridDim.x * U) {
         float2 pf0 = make_float2(0.f, 0.f), pf1 = pf0;
-        if (warp == 0 && valid) {
-            if (2 * c < NB) pf0 = pre(r0, r1, 2 * c);
-            if (2 * c + 1 < NB) pf1 = pre(r0, r1, 2 * c + 1);
+        int my_r0 = 0;
+        bool my_valid = false;
+        if (warp < U && u0 + warp < n_units) {
+            my_r0 = (u0 + warp) * unit_rows + g * row_stride;
+            my_valid = my_r0 < primary_limit;
+            if (my_valid) {
+                if (2 * c < NB) pf0 = pre(my_r0, my_r0 + pair_off, 2 * c);
+                if (2 * c + 1 < NB) pf1 = pre(my_r0, my_r0 + pair_off, 2 * c + 1);
+            }
         }
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        float d[U][4];
+#pragma unroll
+        for (int i = 0; i < U; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
         for (int blk = warp; blk < nblk; blk += T2S_WARPS) {
-            const __nv_bfloat16* pa = W + static_cast<size_t>(r0l) * ldw + blk * 64 + 8 * c;
-            const __nv_bfloat16* pb = W + static_cast<size_t>(r0l + pair_off) * ldw + blk * 64 + 8 * c;
-            const uint4 p0 = t2s_ld_stream(pa), p1 = t2s_ld_stream(pa + 32);
-            const uint4 s0 = t2s_ld_stream(pb), s1 = t2s_ld_stream(pb + 32);
+            uint4 p0[U], p1[U], s0[U], s1[U];
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                int r0 = (u0 + i) * unit_rows + g * row_stride;
+                if (u0 + i >= n_units || r0 >= primary_limit) r0 = 0;
+                const __nv_bfloat16* pa = W + static_cast<size_t>(r0) * ldw + blk * 64 + 8 * c;
+                const __nv_bfloat16* pb = W + static_cast<size_t>(r0 + pair_off) * ldw + blk * 64 + 8 * c;
+                p0[i] = t2s_ld_stream(pa), p1[i] = t2s_ld_stream(pa + 32);
+                s0[i] = t2s_ld_stream(pb), s1[i] = t2s_ld_stream(pb + 32);
+            }
             const uint2* xb = reinterpret_cast<const uint2*>(sxb + g * ldxb + blk * 64 + 4 * c);
             const uint2 x0 = xb[0], x1 = xb[4], x2 = xb[8], x3 = xb[12];
-            t2s_mma_bf16(d, p0.x, s0.x, p0.y, s0.y, x0.x, x0.y);
-            t2s_mma_bf16(d, p0.z, s0.z, p0.w, s0.w, x1.x, x1.y);
-            t2s_mma_bf16(d, p1.x, s1.x, p1.y, s1.y, x2.x, x2.y);
-            t2s_mma_bf16(d, p1.z, s1.z, p1.w, s1.w, x3.x, x3.y);
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                t2s_mma_bf16(d[i], p0[i].x, s0[i].x, p0[i].y, s0[i].y, x0.x, x0.y);
+                t2s_mma_bf16(d[i], p0[i].z, s0[i].z, p0[i].w, s0[i].w, x1.x, x1.y);
+                t2s_mma_bf16(d[i], p1[i].x, s1[i].x, p1[i].y, s1[i].y, x2.x, x2.y);
+                t2s_mma_bf16(d[i], p1[i].z, s1[i].z, p1[i].w, s1[i].w, x3.x, x3.y);
+            }
         }
-        sfrag[warp * 32 + lane] = make_float4(d[0], d[1], d[2], d[3]);
+#pragma unroll
+        for (int i = 0; i < U; ++i) sfrag[(i * T2S_WARPS + warp) * 32 + lane] = make_float4(d[i][0], d[i][1], d[i][2], d[i][3]);
         __syncthreads();
-        if (warp == 0) {
-            const int nw = nblk < T2S_WARPS ? nblk : T2S_WARPS;
-            float4 acc = sfrag[lane];
+        if (warp < U && u0 + warp < n_units) {
+            const float4* sf = sfrag + warp * T2S_WARPS * 32;
+            float4 acc = sf[lane];
             for (int w = 1; w < nw; ++w) {
-                const float4 v = sfrag[w * 32 + lane];
+                const float4 v = sf[w * 32 + lane];
                 acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
             }
-            if (valid) {
-                if (2 * c < NB) epi(r0, r1, 2 * c, acc.x, acc.z, pf0);
-                if (2 * c + 1 < NB) epi(r0, r1, 2 * c + 1, acc.y, acc.w, pf1);
+            if (my_valid) {
+                if (2 * c < NB) epi(my_r0, my_r0 + pair_off, 2 * c, acc.x, acc.z, pf0);
+                if (2 * c + 1 < NB) epi(my_r0, my_r0 + pair_off, 2 * c + 1, acc.y, acc.w, pf1);
             }
         }
         __syncthreads();
     }
+}
+
+template <int NB, class Pre, class Epi>
+__device__ __forceinline__ void t2s_gemv_mma(const __nv_bfloat16* __restrict__ W, int ldw, int n_units, int unit_rows,
+                                             int row_stride, int pair_off, int primary_limit, int K,
+                                             const __nv_bfloat16* sxb, int ldxb, float4* sfrag, Pre pre, Epi epi) {
+    if (t2s_dbg_skip_gemv) return;
+    const int per_cta = (n_units + gridDim.x - 1) / gridDim.x;
+    if (per_cta <= 1) t2s_gemv_mma_u<NB, 1>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, sxb, ldxb, sfrag, pre, epi);
+    else if (per_cta <= 2) t2s_gemv_mma_u<NB, 2>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, sxb, ldxb, sfrag, pre, epi);
+    else t2s_gemv_mma_u<NB, 3>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, sxb, ldxb, sfrag, pre, epi);
 }
 
 // L2 prefetch of the rows of this CTA's units in the next tensor-core stage
@@ -655,12 +682,17 @@ __device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB,
             const int j = kb + lane;
             const int cnt = min(32, nkeys - kb);
             float sc = NEG;
+            uint32_t vw[KV16 ? 32 : 1];
             if constexpr (KV16) {
                 // a lane owns key kb + lane: one coalesced 4-byte word (two dims) per load, 32 loads
                 const uint32_t* Kw = static_cast<const uint32_t*>(Kc) + (static_cast<size_t>(bh) * (n_alloc / 32) + kb / 32) * 1024 + lane;
                 uint32_t kw[32];
 #pragma unroll
                 for (int d = 0; d < 32; ++d) kw[d] = __ldcg(Kw + d * 32);
+                // the V rows do not depend on the scores: request them now, one memory round trip for both
+                const uint32_t* vr = static_cast<const uint32_t*>(Vc) + (static_cast<size_t>(bh) * n_alloc + kb) * 32 + lane;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) vw[t] = t < cnt ? __ldcg(vr + t * 32) : 0u;
                 float acc = 0.f;
 #pragma unroll
                 for (int d = 0; d < 32; ++d) {
@@ -699,10 +731,6 @@ __device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB,
             T2S_AMARK(3);
             float2 ob = make_float2(0.f, 0.f);
             if constexpr (KV16) {
-                const uint32_t* vr = static_cast<const uint32_t*>(Vc) + (static_cast<size_t>(bh) * n_alloc + kb) * 32 + lane;
-                uint32_t vw[32];
-#pragma unroll
-                for (int t = 0; t < 32; ++t) vw[t] = t < cnt ? __ldcg(vr + t * 32) : 0u;
 #pragma unroll
                 for (int t = 0; t < 32; ++t) {
                     const float pt = __shfl_sync(0xffffffffu, p, t);
@@ -918,7 +946,7 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
     float* sx = smem;                                  // [NB][ldx] fp32  /  [8][ldxb] bf16 (same storage)
     __nv_bfloat16* sxb = reinterpret_cast<__nv_bfloat16*>(smem);
     float* spart = sx + (kMMA && 4 * ldxb > NB * ldx ? 4 * ldxb : NB * ldx);   // [16][32] float4: attention partials, sampler histogram, MMA fragments
-    float* sq = spart + T2S_WARPS * 32 * 4;            // [64]
+    float* sq = spart + 3 * T2S_WARPS * 32 * 4;        // [64]
     float* sred = sq + T2S_DH;                         // [NB * 16]
     float* sscale = sred + NB * T2S_WARPS;             // [8]
     int* sidx = reinterpret_cast<int*>(sscale + 8);    // [2 + 16]
@@ -1232,7 +1260,7 @@ inline size_t t2s_decode_smem(const covo_t2s* h, int NB) {
     size_t act = sizeof(float) * static_cast<size_t>(NB) * kmax;                  // fp32 rows
     const size_t act16 = 2 * static_cast<size_t>(8) * (kmax + 16);                // 8 bf16 rows (tensor-core path)
     if (act16 > act) act = act16;
-    return act + sizeof(float) * (T2S_WARPS * 32 * 4 + T2S_DH + NB * T2S_WARPS + 8 + 2 + T2S_WARPS + 2);
+    return act + sizeof(float) * (3 * T2S_WARPS * 32 * 4 + T2S_DH + NB * T2S_WARPS + 8 + 2 + T2S_WARPS + 2);
 }
 
 // Workspace layout for (B rows padded to NB, S1 text positions incl. EOS, max_len decode positions)
