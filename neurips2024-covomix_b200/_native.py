@@ -2,7 +2,7 @@
 
 There is no CPU or PyTorch fallback: if the library has not been built, or the device is not
 sm_100, every entry point raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
-(or ``make -C neurips2024-covomix_b200/csrc``).
+(one nvcc invocation on ``csrc/covomix_b200.cu``, flags in ``__graft_entry__.NVCC_FLAGS``).
 """
 from __future__ import annotations
 
