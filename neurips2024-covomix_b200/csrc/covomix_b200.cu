@@ -28,6 +28,10 @@ int init_kernel_attrs() {
     COVO_TRY((set_gemm_attr<128, 0>()));
     COVO_TRY((set_gemm_attr<64, 0>()));
     COVO_CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    COVO_CK(cudaFuncSetAttribute(hifigan_fused_last_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(HF_SMEM_BYTES)));
+    COVO_CK(cudaFuncSetAttribute(hifigan_fused_last_stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(HF_SMEM_BYTES)));
     return COVO_OK;
 }
 
@@ -167,6 +171,7 @@ int covo_hifigan_create(const covo_hifigan_cfg* cfg, const void* packed_weights,
     covo_hifigan* h = new covo_hifigan();
     h->cfg = *cfg;
     h->is_fp16 = cfg->h_format == COVO_H_FP16;
+    h->allow_fused = !env_flag("COVO_HIFIGAN_NO_FUSED");
     h->mel_pad = pad64(cfg->num_mels);
     int rc = check_device(device, &h->di);
     if (rc == COVO_OK) rc = init_kernel_attrs();
@@ -205,7 +210,9 @@ int covo_hifigan_launches_per_forward(const covo_hifigan* h) {
     if (!h) return 0;
     const covo_hifigan_cfg& c = h->cfg;
     const int per_rb = c.num_dilations * (c.resblock_type == 1 ? 2 : 1);
-    return 2 + c.num_upsamples * (1 + c.num_kernels * per_rb + 1) + 1;
+    const int layered = 2 + c.num_upsamples * (1 + c.num_kernels * per_rb + 1) + 1;
+    // fused last stage: its convs, the stage mean and conv_post are one launch
+    return hifi_fused_eligible(h) ? layered - (c.num_kernels * per_rb + 2) + 1 : layered;
 }
 
 int covo_hifigan_forward(covo_hifigan* h, const float* mel, void* wav, int B, int T, int out_dtype, void* workspace,

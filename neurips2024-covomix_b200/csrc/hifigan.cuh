@@ -4,6 +4,7 @@
 // tcgen05 implicit-GEMM kernel (gemm_sm100.cuh) with LeakyReLU / bias / residual fused in its epilogue.
 #pragma once
 #include "common.cuh"
+#include "hifigan_fused.cuh"
 
 namespace covo {
 
@@ -29,6 +30,9 @@ struct HifiPlan {
     GemmOp pre;
     std::vector<HifiStage> stages;
     int launches = 0;
+    bool fused_last = false;       // last stage (resblocks + mean + conv_post + tanh) runs as hifigan_fused_last_stage_kernel
+    HifiFusedArgs fused;
+    double fused_flops = 0.0;
 };
 
 }  // namespace covo
@@ -39,6 +43,7 @@ struct covo_hifigan {
     covo::Weights w;
     int mel_pad = 0;
     int is_fp16 = 0;
+    bool allow_fused = true;       // COVO_HIFIGAN_NO_FUSED=1 keeps the layer-by-layer path for the last stage
     std::vector<covo::HifiPlan*> plans;
 };
 
@@ -137,6 +142,26 @@ inline int hifi_conv_out(const covo_hifigan* h, GemmOp& op, float* out_f32, cons
 }
 inline double conv_flops(int B, int T, int cin, int cout, int k) { return 2.0 * B * T * static_cast<double>(cin) * cout * k; }
 
+// The fused last-stage kernel covers ResBlock1 stages of <= 32 channels whose receptive field fits its tile
+// (config_covomix.json: 31 channels, k = 3/7/11, dilations 1/3/5: halo 60, tap reach 25).
+inline bool hifi_fused_eligible(const covo_hifigan* h) {
+    const covo_hifigan_cfg& c = h->cfg;
+    if (!h->allow_fused || c.resblock_type != 1 || c.num_kernels > 3 || c.num_dilations > 4) return false;
+    if (hifi_chan(c, c.num_upsamples - 1) > HF_C) return false;
+    for (int j = 0; j < c.num_kernels; ++j) {
+        const int k = c.resblock_kernel_sizes[j];
+        if (k > HF_MAXK || k % 2 == 0) return false;
+        int halo = 0;
+        for (int m = 0; m < c.num_dilations; ++m) {
+            const int d = c.resblock_dilations[j][m];
+            if ((k - 1) / 2 * d > HF_MARGIN) return false;
+            halo += (k - 1) / 2 * d + (k - 1) / 2;
+        }
+        if (2 * (halo + 3) + HF_TP > HF_R) return false;
+    }
+    return true;
+}
+
 inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
     const covo_hifigan_cfg& c = h->cfg;
     const Weights& w = h->w;
@@ -188,8 +213,54 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
             op.cat = PC_GEMM_VOC;
             ++p.launches;
         }
-        // ---- resblocks
+        // ---- narrow last stage: one fused kernel instead of 6 * num_kernels GEMM launches + mean + conv_post
         s.convs.clear();
+        if (i + 1 == c.num_upsamples && hifi_fused_eligible(h)) {
+            HifiFusedArgs& f = p.fused;
+            memset(&f, 0, sizeof(f));
+            f.x = s.x;
+            f.nk = c.num_kernels;
+            f.nd = c.num_dilations;
+            f.T = s.t_out;
+            f.ldx = s.c_out_pad;
+            f.ld_post = s.c_out_pad;
+            f.H = 0;
+            f.inv_nk = 1.0f / static_cast<float>(c.num_kernels);
+            f.slope_res = 0.1f;
+            f.slope_post = 0.01f;                       // F.leaky_relu default before conv_post (models.py:112)
+            p.fused_flops = conv_flops(p.B, s.t_out, s.c_out, 1, 7);
+            for (int j = 0; j < c.num_kernels; ++j) {
+                const int k = c.resblock_kernel_sizes[j];
+                const int r = i * c.num_kernels + j;
+                f.ksize[j] = k;
+                f.halo[j] = 0;
+                for (int m = 0; m < c.num_dilations; ++m) {
+                    const int d = c.resblock_dilations[j][m];
+                    f.dil[j][m] = d;
+                    f.halo[j] += (k - 1) / 2 * d + (k - 1) / 2;
+                    Tensor t1, t2, u1, u2;
+                    COVO_TRY(w.get("rb." + std::to_string(r) + ".c1." + std::to_string(m) + ".w", hdt, &t1));
+                    COVO_TRY(w.get("rb." + std::to_string(r) + ".c1." + std::to_string(m) + ".b", DT_F32, &u1));
+                    COVO_TRY(w.get("rb." + std::to_string(r) + ".c2." + std::to_string(m) + ".w", hdt, &t2));
+                    COVO_TRY(w.get("rb." + std::to_string(r) + ".c2." + std::to_string(m) + ".b", DT_F32, &u2));
+                    f.w1[j][m] = t1.ptr;
+                    f.w2[j][m] = t2.ptr;
+                    f.b1[j][m] = u1.as<float>();
+                    f.b2[j][m] = u2.as<float>();
+                    p.fused_flops += 2.0 * conv_flops(p.B, s.t_out, s.c_out, s.c_out, k);
+                }
+                if (f.halo[j] > f.H) f.H = f.halo[j];
+            }
+            Tensor pw, pb;
+            COVO_TRY(w.get("conv_post.w", DT_F32, &pw));
+            COVO_TRY(w.get("conv_post.b", DT_F32, &pb));
+            f.wpost = pw.as<float>();
+            f.bpost = pb.as<float>();
+            p.fused_last = true;
+            p.launches += 1;
+            continue;
+        }
+        // ---- resblocks
         for (int j = 0; j < c.num_kernels; ++j) {
             const int k = c.resblock_kernel_sizes[j];
             const int r = i * c.num_kernels + j;
@@ -235,7 +306,7 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
         }
         p.launches += static_cast<int>(s.convs.size()) + 1;     // + stage mean
     }
-    p.launches += 1;                                            // conv_post
+    if (!p.fused_last) p.launches += 1;                         // conv_post
     return COVO_OK;
 }
 
@@ -283,6 +354,17 @@ inline int hifi_enqueue(covo_hifigan* h, HifiPlan& p, const float* mel, void* wa
     for (int i = 0; i < c.num_upsamples; ++i) {
         HifiStage& s = p.stages[i];
         COVO_TRY(launch_gemm(s.up, st));
+        if (p.fused_last && i + 1 == c.num_upsamples) {
+            HifiFusedArgs f = p.fused;
+            f.wav = wav;
+            f.out_dtype = out_dtype;
+            ProfScope ps(PC_GEMM_VOC, p.fused_flops, st);
+            dim3 g(ceil_div(s.t_out, HF_TP), p.B);
+            if (h->is_fp16) hifigan_fused_last_stage_kernel<true><<<g, HF_THREADS, HF_SMEM_BYTES, st>>>(f);
+            else hifigan_fused_last_stage_kernel<false><<<g, HF_THREADS, HF_SMEM_BYTES, st>>>(f);
+            COVO_CK(cudaGetLastError());
+            return COVO_OK;
+        }
         for (const GemmOp& op : s.convs) COVO_TRY(launch_gemm(op, st));
         const size_t n4 = static_cast<size_t>(p.B) * s.t_out * s.c_out_pad / 4;
         const float slope = (i + 1 == c.num_upsamples) ? 0.01f : 0.1f;     // models.py:103 vs :112 (F.leaky_relu default)
