@@ -468,14 +468,19 @@ def run_vocoder_sweep(args):
             # bytes moved by the layer-by-layer schedule: per output sample-channel of a stage with C padded channels
             c_pad, t_len, byt = [512, 256, 128, 64, 64], T, 0.0
             byt += B * T * (80 * 4 + 128 * 2 + 128 * 2 + c_pad[0] * 2)
+            fused_last = not os.environ.get("COVO_HIFIGAN_NO_FUSED")        # last stage = one tile-resident kernel
             for i, (u, k) in enumerate(zip((5, 4, 4, 2), (8, 8, 4, 4))):
                 t_out = (t_len - 1) * u - 2 * ((k - u) // 2) + k
                 n = B * t_out * c_pad[i + 1]
                 byt += B * t_len * c_pad[i] * 2 + n * 6                      # upsample: read in, write f32 + 16-bit
-                byt += 3 * (3 * (n * 2 + n * 2) + 3 * (n * 2 + n * 4 + n * 4 + n * 2))   # 3 resblocks x 3 x (c1: r+w, c2: r + res + w f32 + w h)
-                byt += 3 * n * 4 + n * 2                                      # stage mean
+                if fused_last and i == 3:
+                    byt += B * t_out * (32 * 4 * 382 / 256 + 4)             # stage input once (x halo) + waveform
+                else:
+                    byt += 3 * (3 * (n * 2 + n * 2) + 3 * (n * 2 + n * 4 + n * 4 + n * 2))   # 3 resblocks x 3 x (c1: r+w, c2: r + res + w f32 + w h)
+                    byt += 3 * n * 4 + n * 2                                  # stage mean
                 t_len = t_out
-            byt += B * t_len * (64 * 2 * 1 + 4)
+            if not fused_last:
+                byt += B * t_len * (64 * 2 * 1 + 4)
             line = {"metric": "audio-seconds/sec (RTF), HiFi-GAN only", "workload": "C5 vocoder sweep", "T": T, "B": B,
                     "ms": ms, "value": B * T / FRAME_RATE / (ms * 1e-3), "unit": "audio-s/s",
                     "achieved_tflops": flops / (ms * 1e-3) / 1e12, "frac_of_tensor_peak": flops / (ms * 1e-3) / 1e12 / pk["tflops"],
