@@ -401,12 +401,12 @@ __device__ __forceinline__ void t2s_gemv_rows(const WT* __restrict__ W, int ldw,
 // Tensor-core path for wide batches (bf16 matrices, NB >= 4).  With 8 rows of activations the CUDA-core product above is
 // bound by shared-memory reads and FMA issue (16 LDS.128 + 128 FMA per 16-byte weight load); a warp-level
 // mma.sync m16n8k16 takes the batch as its n = 8 dimension instead: A = 16 weight rows x 16 k (bf16, straight from global
-// memory), B = 16 k x 8 batch rows (bf16 activations in shared memory), D = 16 x 8 fp32.  (tcgen05 wants M >= 64 rows of
+// memory), B = 16 k x 8 batch rows (activations rounded to bf16 in registers), D = 16 x 8 fp32.  (tcgen05 wants M >= 64 rows of
 // the *moving* operand per CTA and a TMEM round trip per stage; for a 16 x 8 x K product that is re-launched 26 times per
 // decoding step behind a grid barrier, the register-resident warp MMA is the right tool.)
 //  * k is permuted inside every 64-k block so that a lane's A fragments for four consecutive MMAs are two contiguous
-//    16-byte loads per row (lane c of a quad owns k [8c, 8c+8) and [32+8c, 32+8c+8)), and the activations are stored in the
-//    matching "MMA order" so that a quad reads 32 contiguous bytes per MMA (t2s_mma_pos);
+//    16-byte loads per row (lane c of a quad owns k [8c, 8c+8) and [32+8c, 32+8c+8)); the lane fetches the matching
+//    activations of its batch row (4 x 16 bytes of fp32, t2s_mma_kofs) straight from global memory next to its weight loads;
 //  * a unit = 8 primary rows + 8 secondary rows (A rows 0-7 / 8-15), so a lane ends up with a (primary, secondary) pair for
 //    two batch rows -- exactly what the rotary / GEGLU / two-plain-rows epilogues of the CUDA-core path take;
 //  * the 16 warps of a CTA split K of ONE unit (one 64-k block each for K = 1024) and reduce their D fragments through
@@ -418,17 +418,18 @@ __device__ __forceinline__ void t2s_mma_bf16(float (&d)[4], uint32_t a0, uint32_
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// position (in elements) of physical k (multiple of 4) inside the MMA-ordered activation row
-__device__ __forceinline__ int t2s_mma_pos(int k) {
-    const int q = (k >> 2) & 15;                                  // 4-element group inside the 64-k block
-    const int c = (q & 7) >> 1, s = (q & 1) | ((q >> 3) << 1);    // owning lane of the quad, MMA index
-    return (k & ~63) + 16 * s + 4 * c;
-}
+// physical k (offset inside a 64-k block) of the 4 consecutive activations lane c of a quad feeds to MMA s
+__device__ __forceinline__ int t2s_mma_kofs(int c, int s) { return (s < 2 ? 0 : 32) + 8 * c + 4 * (s & 1); }
 
+// xg: fp32 activations [NB][K] in GLOBAL memory (written by other CTAs in the previous stage, read with ld.cg); gamma:
+// RMSNorm gain [K] or nullptr.  A lane fetches exactly the 4 x 4 activations of its batch row that its MMAs need, next to
+// its weight loads (no staging pass through shared memory, no extra block sync), multiplies by gamma and rounds to bf16.
+// With gamma the row factor sqrt(K) / ||x|| of RMSNorm (text2semantic.py:143-151) is applied to the sums: the 16 warps of the
+// CTA read every element of the rows exactly once per round, so sum(x^2) rides along with the fragment exchange.
 template <int NB, int U, class Pre, class Epi>
 __device__ __forceinline__ void t2s_gemv_mma_u(const __nv_bfloat16* __restrict__ W, int ldw, int n_units, int unit_rows,
-                                               int row_stride, int pair_off, int primary_limit, int K,
-                                               const __nv_bfloat16* sxb, int ldxb, float4* sfrag, Pre pre, Epi epi) {
+                                               int row_stride, int pair_off, int primary_limit, int K, const float* xg,
+                                               const float* __restrict__ gamma, float4* sfrag, float* sssq, Pre pre, Epi epi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, c = lane & 3;
     const int nblk = K / 64;
@@ -449,6 +450,7 @@ __device__ __forceinline__ void t2s_gemv_mma_u(const __nv_bfloat16* __restrict__
         float d[U][4];
 #pragma unroll
         for (int i = 0; i < U; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+        float ss = 0.f;
         for (int blk = warp; blk < nblk; blk += T2S_WARPS) {
             uint4 p0[U], p1[U], s0[U], s1[U];
 #pragma unroll
@@ -460,18 +462,40 @@ __device__ __forceinline__ void t2s_gemv_mma_u(const __nv_bfloat16* __restrict__
                 p0[i] = t2s_ld_stream(pa), p1[i] = t2s_ld_stream(pa + 32);
                 s0[i] = t2s_ld_stream(pb), s1[i] = t2s_ld_stream(pb + 32);
             }
-            const uint2* xb = reinterpret_cast<const uint2*>(sxb + g * ldxb + blk * 64 + 4 * c);
-            const uint2 x0 = xb[0], x1 = xb[4], x2 = xb[8], x3 = xb[12];
+            float4 xv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g < NB) xv[q] = __ldcg(reinterpret_cast<const float4*>(xg + static_cast<size_t>(g) * K + blk * 64 + t2s_mma_kofs(c, q)));
+            }
+            uint32_t xb[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 v = xv[q];
+                ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+                if (gamma != nullptr) {
+                    const float4 gm = *reinterpret_cast<const float4*>(gamma + blk * 64 + t2s_mma_kofs(c, q));
+                    v.x *= gm.x, v.y *= gm.y, v.z *= gm.z, v.w *= gm.w;
+                }
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                xb[q][0] = *reinterpret_cast<const uint32_t*>(&lo);
+                xb[q][1] = *reinterpret_cast<const uint32_t*>(&hi);
+            }
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                t2s_mma_bf16(d[i], p0[i].x, s0[i].x, p0[i].y, s0[i].y, x0.x, x0.y);
-                t2s_mma_bf16(d[i], p0[i].z, s0[i].z, p0[i].w, s0[i].w, x1.x, x1.y);
-                t2s_mma_bf16(d[i], p1[i].x, s1[i].x, p1[i].y, s1[i].y, x2.x, x2.y);
-                t2s_mma_bf16(d[i], p1[i].z, s1[i].z, p1[i].w, s1[i].w, x3.x, x3.y);
+                t2s_mma_bf16(d[i], p0[i].x, s0[i].x, p0[i].y, s0[i].y, xb[0][0], xb[0][1]);
+                t2s_mma_bf16(d[i], p0[i].z, s0[i].z, p0[i].w, s0[i].w, xb[1][0], xb[1][1]);
+                t2s_mma_bf16(d[i], p1[i].x, s1[i].x, p1[i].y, s1[i].y, xb[2][0], xb[2][1]);
+                t2s_mma_bf16(d[i], p1[i].z, s1[i].z, p1[i].w, s1[i].w, xb[3][0], xb[3][1]);
             }
         }
 #pragma unroll
         for (int i = 0; i < U; ++i) sfrag[(i * T2S_WARPS + warp) * 32 + lane] = make_float4(d[i][0], d[i][1], d[i][2], d[i][3]);
+        if (gamma != nullptr) {       // sum(x^2) of batch row g over this warp's blocks: reduce the quad, one slot per (warp, row)
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            if (c == 0) sssq[warp * 8 + g] = ss;
+        }
         __syncthreads();
         if (warp < U && u0 + warp < n_units) {
             const float4* sf = sfrag + warp * T2S_WARPS * 32;
@@ -479,6 +503,17 @@ __device__ __forceinline__ void t2s_gemv_mma_u(const __nv_bfloat16* __restrict__
             for (int w = 1; w < nw; ++w) {
                 const float4 v = sf[w * 32 + lane];
                 acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+            }
+            if (gamma != nullptr) {
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                for (int w = 0; w < T2S_WARPS; ++w) {
+                    t0 += sssq[w * 8 + 2 * c];
+                    t1 += sssq[w * 8 + 2 * c + 1];
+                }
+                const float sc0 = sqrtf(static_cast<float>(K)) / fmaxf(sqrtf(t0), 1e-12f);
+                const float sc1 = sqrtf(static_cast<float>(K)) / fmaxf(sqrtf(t1), 1e-12f);
+                acc.x *= sc0, acc.z *= sc0, acc.y *= sc1, acc.w *= sc1;
             }
             if (my_valid) {
                 if (2 * c < NB) epi(my_r0, my_r0 + pair_off, 2 * c, acc.x, acc.z, pf0);
@@ -491,13 +526,13 @@ __device__ __forceinline__ void t2s_gemv_mma_u(const __nv_bfloat16* __restrict__
 
 template <int NB, class Pre, class Epi>
 __device__ __forceinline__ void t2s_gemv_mma(const __nv_bfloat16* __restrict__ W, int ldw, int n_units, int unit_rows,
-                                             int row_stride, int pair_off, int primary_limit, int K,
-                                             const __nv_bfloat16* sxb, int ldxb, float4* sfrag, Pre pre, Epi epi) {
+                                             int row_stride, int pair_off, int primary_limit, int K, const float* xg,
+                                             const float* __restrict__ gamma, float4* sfrag, float* sssq, Pre pre, Epi epi) {
     if (t2s_dbg_skip_gemv) return;
     const int per_cta = (n_units + gridDim.x - 1) / gridDim.x;
-    if (per_cta <= 1) t2s_gemv_mma_u<NB, 1>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, sxb, ldxb, sfrag, pre, epi);
-    else if (per_cta <= 2) t2s_gemv_mma_u<NB, 2>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, sxb, ldxb, sfrag, pre, epi);
-    else t2s_gemv_mma_u<NB, 3>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, sxb, ldxb, sfrag, pre, epi);
+    if (per_cta <= 1) t2s_gemv_mma_u<NB, 1>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, xg, gamma, sfrag, sssq, pre, epi);
+    else if (per_cta <= 2) t2s_gemv_mma_u<NB, 2>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, xg, gamma, sfrag, sssq, pre, epi);
+    else t2s_gemv_mma_u<NB, 3>(W, ldw, n_units, unit_rows, row_stride, pair_off, primary_limit, K, xg, gamma, sfrag, sssq, pre, epi);
 }
 
 // L2 prefetch of the rows of this CTA's units in the next tensor-core stage
@@ -514,53 +549,6 @@ __device__ __forceinline__ void t2s_prefetch_team(const void* W, int row_bytes, 
             const char* row = base + static_cast<size_t>(r0 + (rr >> 3) * pair_off) * row_bytes + ln * 128;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
         }
-    }
-}
-
-// bf16 activations in MMA order: sxb[b][t2s_mma_pos(j)] = bf16(x[b][j] * gamma[j]) (gamma == nullptr: plain copy; sscale is
-// only written with gamma).  Rows NB..7 of sxb stay zero (cleared once at kernel start).  D % 64 == 0.
-template <int NB>
-__device__ __forceinline__ void t2s_load_bf16(const float* x, const float* __restrict__ gamma, int D, __nv_bfloat16* sxb,
-                                              int ldxb, float* sred, float* sscale) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float ss[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) ss[b] = 0.f;
-    for (int j = tid * 4; j < D; j += T2S_THREADS * 4) {
-        float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (gamma != nullptr) g = *reinterpret_cast<const float4*>(gamma + j);
-        float4 v[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) v[b] = __ldcg(reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * D + j));
-        const int dst = t2s_mma_pos(j);
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v[b].x * g.x, v[b].y * g.y);
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(v[b].z * g.z, v[b].w * g.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(sxb + b * ldxb + dst) = pk;
-            ss[b] = fmaf(v[b].x, v[b].x, fmaf(v[b].y, v[b].y, fmaf(v[b].z, v[b].z, fmaf(v[b].w, v[b].w, ss[b]))));
-        }
-    }
-    if (gamma != nullptr) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
-            if (lane == 0) sred[b * T2S_WARPS + warp] = ss[b];
-        }
-    }
-    __syncthreads();
-    if (gamma != nullptr) {
-        if (tid < NB) {
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < T2S_WARPS; ++w) t += sred[tid * T2S_WARPS + w];
-            sscale[tid] = sqrtf(static_cast<float>(D)) / fmaxf(sqrtf(t), 1e-12f);
-        }
-        __syncthreads();
     }
 }
 
@@ -942,14 +930,13 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
     extern __shared__ __align__(16) float smem[];
     const int kmax = a.ffi_pad > a.Dt ? a.ffi_pad : a.Dt;
     const int ldx = kmax;                              // fp32 activation rows (CUDA-core path, and the logit stage)
-    const int ldxb = kmax + 16;                        // bf16 activation rows, 32 bytes past a multiple of 128 (conflict-free)
-    float* sx = smem;                                  // [NB][ldx] fp32  /  [8][ldxb] bf16 (same storage)
-    __nv_bfloat16* sxb = reinterpret_cast<__nv_bfloat16*>(smem);
-    float* spart = sx + (kMMA && 4 * ldxb > NB * ldx ? 4 * ldxb : NB * ldx);   // [16][32] float4: attention partials, sampler histogram, MMA fragments
+    float* sx = smem;                                  // [NB][ldx] fp32 (CUDA-core path and the logit stage)
+    float* spart = sx + NB * ldx;                      // 3 x [16][32] float4: attention partials, sampler histogram, MMA fragments
     float* sq = spart + 3 * T2S_WARPS * 32 * 4;        // [64]
     float* sred = sq + T2S_DH;                         // [NB * 16]
     float* sscale = sred + NB * T2S_WARPS;             // [8]
-    int* sidx = reinterpret_cast<int*>(sscale + 8);    // [2 + 16]
+    int* sidx = reinterpret_cast<int*>(sscale + 8);    // [2 + 16 + 2]
+    float* sssq = reinterpret_cast<float*>(sidx + 20); // [16 warps][8 rows] sum(x^2) partials (tensor-core path)
     float4* sfrag = reinterpret_cast<float4*>(spart);
     unsigned epoch = 0;
     const int tid = threadIdx.x;
@@ -960,9 +947,13 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
     const auto resid = [=](int r, int b) { return __ldcg(x + b * Dt + r); };
 
     // activation staging for a projection with K inputs: RMSNorm'ed (gamma != nullptr) or plain
+    const float* cur_src = nullptr;                    // tensor-core path: the projection reads its activations itself
+    const float* cur_gamma = nullptr;
     auto stage_in = [&](const float* src, const float* gamma, int K) {
         if constexpr (kMMA) {
-            t2s_load_bf16<NB>(src, gamma, K, sxb, ldxb, sred, sscale);
+            cur_src = src;
+            cur_gamma = gamma;
+            (void)K;
         } else {
             if (gamma != nullptr) t2s_load_norm<NB>(src, gamma, K, t2s_half<WT>(K), sx, ldx, sred, sscale);
             else t2s_load_plain<NB>(src, K, t2s_half<WT>(K), sx, ldx);
@@ -971,7 +962,7 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
     // a plain projection: n_rows rows of W [n_rows, K]; epi1(r, b, v, prefetched), pre1(r, b)
     auto proj_rows = [&](const void* W, int n_rows, int K, auto pre1, auto epi1) {
         if constexpr (kMMA) {
-            t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(W), K, n_rows / 16, 16, 1, 8, n_rows, K, sxb, ldxb, sfrag,
+            t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(W), K, n_rows / 16, 16, 1, 8, n_rows, K, cur_src, cur_gamma, sfrag, sssq,
                              [=](int r0, int r1, int b) { return make_float2(pre1(r0, b), pre1(r1, b)); },
                              [=](int r0, int r1, int b, float v0, float v1, float2 pf) {
                                  epi1(r0, b, v0, pf.x);
@@ -990,8 +981,8 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
         else t2s_prefetch_rows(W, Dt * static_cast<int>(sizeof(WT)), 3 * inner / 2, 2, 1, 2);
     };
 
-    if constexpr (kMMA) {      // batch rows NB..7 of the MMA's n dimension: zero, never written again
-        for (int i = tid; i < 8 * ldxb / 2; i += T2S_THREADS) reinterpret_cast<uint32_t*>(sxb)[i] = 0u;
+    if constexpr (kMMA) {      // the tensor-core projections apply the RMSNorm row factor themselves: the epilogues' sscale[b] is 1
+        if (tid < 8) sscale[tid] = 1.0f;
         __syncthreads();
     }
     // position 0 input: the start token (text2semantic.py:746-751)
@@ -1040,8 +1031,8 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
                     }
                 };
                 if constexpr (kMMA)
-                    t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(w.sa_qkv), Dt, 3 * inner / 16, 16, 2, 1, 3 * inner, Dt, sxb,
-                                     ldxb, sfrag, no_pre, epi);
+                    t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(w.sa_qkv), Dt, 3 * inner / 16, 16, 2, 1, 3 * inner, Dt, cur_src,
+                                     cur_gamma, sfrag, sssq, no_pre, epi);
                 else
                     t2s_gemv<WT, NB, 2>(static_cast<const WT*>(w.sa_qkv), Dt, 3 * inner / 2, 2, 1, Dt, sx, ldx, no_pre, epi);
                 prefetch_rows_plain(w.sa_out, inner, Dt);
@@ -1105,8 +1096,8 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
                     hb[b * ffi_pad + r0] = gelu_erf(fmaf(v1, sscale[b], pf.y)) * fmaf(v0, sscale[b], pf.x);
                 };
                 if constexpr (kMMA)
-                    t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(w.ff1), Dt, (a.ffi + 7) / 8, 8, 1, a.ffi, a.ffi, Dt, sxb, ldxb,
-                                     sfrag, pre, epi);
+                    t2s_gemv_mma<NB>(static_cast<const __nv_bfloat16*>(w.ff1), Dt, (a.ffi + 7) / 8, 8, 1, a.ffi, a.ffi, Dt, cur_src,
+                                     cur_gamma, sfrag, sssq, pre, epi);
                 else
                     t2s_gemv<WT, NB, 2>(static_cast<const WT*>(w.ff1), Dt, a.ffi, 1, a.ffi, Dt, sx, ldx, pre, epi);
                 prefetch_rows_plain(w.ff2, ffi_pad, Dt);
@@ -1139,9 +1130,9 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
                                          [=](int r, int b, float v, float) { lg[b * n + r] = v * sscale[b]; });
             }
             prefetch_qkv(a.L[0].sa_qkv);
-            if constexpr (kMMA) {      // the fp32 logit stage used rows NB..7's storage: clear it again for the MMA path
+            if constexpr (kMMA) {      // the fp32 logit stage wrote its row factors: back to 1 for the tensor-core stages
                 __syncthreads();
-                for (int i = tid; i < 8 * ldxb / 2; i += T2S_THREADS) reinterpret_cast<uint32_t*>(sxb)[i] = 0u;
+                if (tid < 8) sscale[tid] = 1.0f;
                 __syncthreads();
             }
         }
@@ -1257,10 +1248,7 @@ inline int t2s_pad_batch(int B) { return B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 
 
 inline size_t t2s_decode_smem(const covo_t2s* h, int NB) {
     const int kmax = h->ffi_pad > h->cfg.target_transformer_dim ? h->ffi_pad : h->cfg.target_transformer_dim;
-    size_t act = sizeof(float) * static_cast<size_t>(NB) * kmax;                  // fp32 rows
-    const size_t act16 = 2 * static_cast<size_t>(8) * (kmax + 16);                // 8 bf16 rows (tensor-core path)
-    if (act16 > act) act = act16;
-    return act + sizeof(float) * (3 * T2S_WARPS * 32 * 4 + T2S_DH + NB * T2S_WARPS + 8 + 2 + T2S_WARPS + 2);
+    return sizeof(float) * (static_cast<size_t>(NB) * kmax + 3 * T2S_WARPS * 32 * 4 + T2S_DH + NB * T2S_WARPS + 8 + 20 + T2S_WARPS * 8);
 }
 
 // Workspace layout for (B rows padded to NB, S1 text positions incl. EOS, max_len decode positions)
