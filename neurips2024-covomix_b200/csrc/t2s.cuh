@@ -324,9 +324,13 @@ __device__ __forceinline__ int t2s_half(int K) {
 // grid CTA-interleaved, so stages with fewer units than warps still pull through every SM.  Lane b < NB first calls
 // pre(r0, r1, b) (a prefetch -- e.g. the residual -- issued BEFORE the weight loads so that its latency hides behind them)
 // and, once the sums are complete, epi(r0, r1, b, v0, v1, prefetched).  K % WVec::N == 0; W rows are 16-byte aligned.
+// Optional grouping (the tied logit projection of the two output streams in one pass): unit u belongs to group
+// u / units_per_group, which reads its activations at sx + group * sx_group_stride and reports rows offset by
+// group * row_group_stride to pre / epi; the weight rows are those of u % units_per_group.
 template <class WT, int NB, int R, class Pre, class Epi>
 __device__ __forceinline__ void t2s_gemv(const WT* __restrict__ W, int ldw, int n_units, int unit_stride, int pair_off, int K,
-                                         const float* sx, int ldx, Pre pre, Epi epi) {
+                                         const float* sx0, int ldx, Pre pre, Epi epi, int units_per_group = 0x7fffffff,
+                                         int sx_group_stride = 0, int row_group_stride = 0) {
     constexpr int VN = WVec<WT>::N;
     const int lane = threadIdx.x & 31;
     const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
@@ -335,9 +339,12 @@ __device__ __forceinline__ void t2s_gemv(const WT* __restrict__ W, int ldw, int 
     const int half = t2s_half<WT>(K);
     if (t2s_dbg_skip_gemv) n_units = 0;
     for (int u = gw; u < n_units; u += GW) {
-        const int r0 = u * unit_stride, r1 = r0 + pair_off;
+        const int grp = u / units_per_group;
+        const int r0 = (u - grp * units_per_group) * unit_stride, r1 = r0 + pair_off;
+        const int rofs = grp * row_group_stride;
+        const float* sx = sx0 + grp * sx_group_stride;
         float2 pf = make_float2(0.f, 0.f);
-        if (lane < NB) pf = pre(r0, r1, lane);
+        if (lane < NB) pf = pre(r0 + rofs, r1 + rofs, lane);
         const WT* w0p = W + static_cast<size_t>(r0) * ldw;
         const WT* w1p = W + static_cast<size_t>(r1) * ldw;
         float acc0[NB], acc1[NB];
@@ -374,26 +381,31 @@ __device__ __forceinline__ void t2s_gemv(const WT* __restrict__ W, int ldw, int 
                 if (R == 2) acc1[b] += __shfl_xor_sync(0xffffffffu, acc1[b], o);
             }
         }
-        if (lane < NB) epi(r0, r1, lane, t2s_select<NB>(acc0, lane), t2s_select<NB>(acc1, lane), pf);
+        if (lane < NB) epi(r0 + rofs, r1 + rofs, lane, t2s_select<NB>(acc0, lane), t2s_select<NB>(acc1, lane), pf);
     }
 }
 
 // A plain projection (no row pairing needed): two adjacent rows per unit when NB >= 4 (halves the shared-memory reads per
 // FMA, which is what bounds the wide-batch stages), one row per unit otherwise (more warps, shorter chains).
 // epi1(r, b, v, prefetched) / pre1(r, b) see single rows.
+// n_groups > 1: the same n_rows weight rows applied to n_groups activation slices sx + g * sx_group_stride; rows are
+// reported as g * n_rows + r.
 template <class WT, int NB, class Pre1, class Epi1>
 __device__ __forceinline__ void t2s_gemv_rows(const WT* __restrict__ W, int ldw, int n_rows, int K, const float* sx, int ldx,
-                                              Pre1 pre1, Epi1 epi1) {
+                                              Pre1 pre1, Epi1 epi1, int n_groups = 1, int sx_group_stride = 0) {
     if (NB >= 4) {
-        t2s_gemv<WT, NB, 2>(W, ldw, n_rows / 2, 2, 1, K, sx, ldx,
+        t2s_gemv<WT, NB, 2>(W, ldw, n_groups * (n_rows / 2), 2, 1, K, sx, ldx,
                             [=](int r0, int r1, int b) { return make_float2(pre1(r0, b), pre1(r1, b)); },
                             [=](int r0, int r1, int b, float v0, float v1, float2 pf) {
                                 epi1(r0, b, v0, pf.x);
                                 epi1(r1, b, v1, pf.y);
-                            });
+                            },
+                            n_rows / 2, sx_group_stride, n_rows);
     } else {
-        t2s_gemv<WT, NB, 1>(W, ldw, n_rows, 1, 0, K, sx, ldx, [=](int r0, int, int b) { return make_float2(pre1(r0, b), 0.f); },
-                            [=](int r0, int, int b, float v0, float, float2 pf) { epi1(r0, b, v0, pf.x); });
+        t2s_gemv<WT, NB, 1>(W, ldw, n_groups * n_rows, 1, 0, K, sx, ldx,
+                            [=](int r0, int, int b) { return make_float2(pre1(r0, b), 0.f); },
+                            [=](int r0, int, int b, float v0, float, float2 pf) { epi1(r0, b, v0, pf.x); }, n_rows,
+                            sx_group_stride, n_rows);
     }
 }
 
@@ -1123,11 +1135,15 @@ __global__ void __launch_bounds__(T2S_THREADS, 1) t2s_decode_kernel(const __grid
         // ---- S9: final norm + tied logit projection per output stream (text2semantic.py:762-776), fp32 table, fp32 activations
         if ((a.dbg_mode & 1) == 0) {
             t2s_load_norm<NB>(a.x, a.final_gamma, Dt, 0, sx, ldx, sred, sscale);
-            for (int s = 0; s < a.n_out; ++s) {
-                float* lg = a.logits + static_cast<size_t>(s) * NB * a.n_logits;
+            {       // both output streams in one pass: group s reads the s-th half of the normalised row
+                float* lg = a.logits;
                 const int n = a.n_logits;
-                t2s_gemv_rows<float, NB>(a.emb, a.demb, a.n_logits, a.demb, sx + s * a.demb, ldx, no_pre1,
-                                         [=](int r, int b, float v, float) { lg[b * n + r] = v * sscale[b]; });
+                t2s_gemv_rows<float, NB>(a.emb, a.demb, a.n_logits, a.demb, sx, ldx, no_pre1,
+                                         [=](int vr, int b, float v, float) {
+                                             const int s = vr / n, r = vr - s * n;
+                                             lg[(static_cast<size_t>(s) * NB + b) * n + r] = v * sscale[b];
+                                         },
+                                         a.n_out, a.demb);
             }
             prefetch_qkv(a.L[0].sa_qkv);
             if constexpr (kMMA) {      // the fp32 logit stage wrote its row factors: back to 1 for the tensor-core stages

@@ -160,3 +160,39 @@ def test_t2s_argument_errors(dev, models):
         m.generate(ids, max_length=8, noise=torch.rand(4, 1, 1, syn.COSINGLE.n_logits))
     with pytest.raises(ValueError):
         m.generate(torch.zeros(9, 4, dtype=torch.long), max_length=4)
+
+
+def test_sm_budget_does_not_change_results(dev, models):
+    """covo_*_set_sm_limit only changes how the persistent kernels' work is dealt to CTAs: the decode loop on 40 SMs gives the
+    same logits (attention grouping depends on the grid, so fp32 summation order may differ), the flow sampler and the
+    vocoder on a reduced grid are bit-identical."""
+    from covomix_b200.t2s import B200TextToSemantic
+    from covomix_b200.flow import B200FlowSampler
+    from covomix_b200.vocoder import B200Generator
+    cfg = syn.COMIX
+    sd, ms = models["comix"]
+    ids = syn.synthetic_text_ids(cfg, 2, 21, seed=6, ragged=True)
+    steps = 40
+    g = torch.Generator().manual_seed(12)
+    u = torch.rand(steps, 2, 2, cfg.n_logits, generator=g)
+    forced = torch.randint(0, 501, (2, 2, steps), generator=g)
+    _, full = ms["bf16"].generate(ids, max_length=steps, noise=u, forced=forced, return_debug=True)
+    small = B200TextToSemantic(sd, cfg, dev, sm_limit=40)
+    _, part = small.generate(ids, max_length=steps, noise=u, forced=forced, return_debug=True)
+    assert part["steps"] == full["steps"]
+    assert rel_l2(part["logits"], full["logits"]) < 1e-4
+    small.close()
+
+    fcfg = syn.VOSINGLE
+    fsd = syn.synthetic_flow_state_dict(fcfg, 1234)
+    fids, cond, y0, mask = syn.synthetic_flow_inputs(fcfg, 2, 300, prompt=50, seed=30)
+    a = B200FlowSampler(fsd, fcfg, dev, torchdiffeq_ode_method="euler", ode_step_size=0.25)
+    b = B200FlowSampler(fsd, fcfg, dev, torchdiffeq_ode_method="euler", ode_step_size=0.25, sm_limit=37)
+    ma = a.sample(phoneme_ids=fids, cond=cond, mask=mask, cond_scale=0.7, y0=y0)
+    mb = b.sample(phoneme_ids=fids, cond=cond, mask=mask, cond_scale=0.7, y0=y0)
+    assert torch.equal(ma, mb)
+    hsd = syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234)
+    mel = syn.synthetic_logmel(torch.Generator().manual_seed(2), 2, 80, 40).to(dev)
+    wa = B200Generator(hsd, syn.HIFIGAN_COVOMIX, dev)(mel)
+    wb = B200Generator(hsd, syn.HIFIGAN_COVOMIX, dev, sm_limit=50)(mel)
+    assert torch.equal(wa, wb)
