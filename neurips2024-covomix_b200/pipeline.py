@@ -77,3 +77,19 @@ def dialogue_item(semantic_a: torch.Tensor, semantic_b: torch.Tensor, mel_prompt
     cond = torch.zeros(n, mel_prompt.shape[1])
     cond[:n_prompt] = mel_prompt
     return {"phoneme_ids": ids, "cond": cond, "mask": mask}
+
+
+def covomix_dialogues(t2s, sampler, generator, texts: Sequence[torch.Tensor], prompts: Sequence[Dict[str, torch.Tensor]],
+                      cond_scale: float = 0.7, batch: int = 8, t2s_kwargs: Dict = None) -> List[np.ndarray]:
+    """The ``covomix(...)`` loop of dialogue_generation.py:283-330 for a LIST of dialogues: per dialogue ``comix_pred`` on the
+    tokenised text (text-to-semantic, one call each -- its EOS rule couples the rows of a batch, so dialogues are decoded
+    one at a time like the reference), ``dialogue_item`` to assemble ids / cond / mask behind the prompt, then ``synthesize``
+    batches equal-length items through the acoustic model and the vocoder.
+
+    texts[i]: Long[S_i] BERT-tokenised text; prompts[i] = {"semantic_a": Long[P], "semantic_b": Long[P], "mel": Float[P, 160]}
+    (``prepare_oracle_hubert`` output for both speakers, cut to the common length and concatenated, :287-297)."""
+    items = []
+    for text, pr in zip(texts, prompts):
+        s1, s2, _ = comix_pred(t2s, text, **(t2s_kwargs or {}))
+        items.append(dialogue_item(pr["semantic_a"], pr["semantic_b"], pr["mel"], s1, s2))
+    return synthesize(sampler, generator, items, cond_scale=cond_scale, batch=batch)

@@ -191,3 +191,30 @@ def test_accelerate_text2semantic_swaps_sample(monkeypatch):
     dropin.accelerate_text2semantic(model, device="cuda:0")
     assert model.cfm_wrapper._b200_t2s.cfg == syn.COMIX
     assert model.cfm_wrapper.sample(grapheme_token_ids=torch.zeros(1, 4)).tolist() == [1, 2, 3]
+
+
+def test_covomix_dialogues_glue_with_fakes():
+    """T2S -> id assembly -> acoustic -> vocoder glue (dialogue_generation.py:283-330) with stand-ins for the three models."""
+    from covomix_b200 import pipeline
+
+    class FakeT2S:
+        def sample(self, ids, **kw):                      # two streams of len(text) tokens, flattened like the reference
+            n = ids.shape[1]
+            return torch.cat((torch.arange(n), torch.arange(n) + 100))
+
+    class FakeSampler:
+        device = torch.device("cpu")
+
+        def sample(self, *, phoneme_ids, cond, mask, cond_scale, **kw):
+            return phoneme_ids[..., 0:1].float().expand(-1, -1, 80).clone()
+
+    class FakeGen:
+        def __call__(self, mel, out_dtype="f32"):
+            return (mel[:, 0, :] * 1.0).to(torch.int16)
+
+    texts = [torch.arange(5), torch.arange(7), torch.arange(5)]
+    prompts = [{"semantic_a": torch.zeros(4, dtype=torch.long), "semantic_b": torch.ones(4, dtype=torch.long),
+                "mel": torch.zeros(3, 160)} for _ in texts]
+    out = pipeline.covomix_dialogues(FakeT2S(), FakeSampler(), FakeGen(), texts, prompts, batch=2)
+    assert [len(o) for o in out] == [5, 7, 5]             # generated frames only (mask), input order kept
+    assert out[1].tolist() == list(range(7))
