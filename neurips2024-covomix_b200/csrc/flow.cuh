@@ -449,7 +449,6 @@ inline void flow_free_plan(FlowPlan* p) {
 // Finds or builds the plan for this call shape.  single_eval: covo_flow_velocity (no graph; t varies per call).
 inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, float cond_scale, int single_eval, void* ws,
                          size_t ws_bytes, FlowPlan** out) {
-    const covo_flow_cfg& c = h->cfg;
     if (B < 1 || N < 1) return fail(COVO_ERR_INVALID, "B=%d N=%d must be positive", B, N);
     if (method != COVO_ODE_EULER && method != COVO_ODE_MIDPOINT) return fail(COVO_ERR_INVALID, "unknown ODE method %d", method);
     const int n_t = single_eval ? 1 : flow_num_times(method, n_steps);
