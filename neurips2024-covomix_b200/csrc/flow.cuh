@@ -347,8 +347,10 @@ inline int flow_enqueue_network(covo_flow* h, FlowPlan& p, int t_idx, cudaStream
     COVO_TRY(launch_gemm(p.op_embed, st));
     {
         ProfScope ps(PC_CONVPOS, 0.0, st);
-        dim3 g(ceil_div(D, 256), ceil_div(p.N, 8), Bt);
-        convpos_kernel<31, 8><<<g, 256, 0, st>>>(p.h0, h->conv_wT.as<float>(), h->conv_b.as<float>(), p.x, p.slots, p.N, D);
+        // 32 positions per thread: 62 window loads per 32 outputs (1.9x read amplification; 8 per thread was 4.75x)
+        constexpr int CONVPOS_TB = 32;
+        dim3 g(ceil_div(D, 256), ceil_div(p.N, CONVPOS_TB), Bt);
+        convpos_kernel<31, CONVPOS_TB><<<g, 256, 0, st>>>(p.h0, h->conv_wT.as<float>(), h->conv_b.as<float>(), p.x, p.slots, p.N, D);
         COVO_CK(cudaGetLastError());
     }
     *launches += 2;
