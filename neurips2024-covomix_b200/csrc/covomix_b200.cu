@@ -352,6 +352,9 @@ int covo_t2s_generate(covo_t2s* h, const int64_t* text_ids, const float* u, cons
         const char* ts = getenv("COVO_T2S_TRACE");
         trace_step = ts ? atoi(ts) : -1;
         COVO_CK(cudaMemcpyToSymbolAsync(t2s_trace_step, &trace_step, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+        const char* ag = getenv("COVO_T2S_ATTN_GROUPS");
+        const int attn_groups = ag ? atoi(ag) : 0;
+        COVO_CK(cudaMemcpyToSymbolAsync(t2s_dbg_attn_groups, &attn_groups, sizeof(int), 0, cudaMemcpyHostToDevice, st));
         const int plain = (a.dbg_mode & 32) ? 1 : 0;
         COVO_CK(cudaMemcpyToSymbolAsync(t2s_dbg_plain_loads, &plain, sizeof(int), 0, cudaMemcpyHostToDevice, st));
         const int no_pf = (a.dbg_mode & 16) ? 1 : 0;

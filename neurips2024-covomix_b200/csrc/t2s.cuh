@@ -173,7 +173,8 @@ __global__ void t2s_ctx_scatter_kernel(const float* __restrict__ kv, const float
 // ======================================================================================================================
 // the persistent decode kernel
 // ======================================================================================================================
-constexpr int T2S_MAXS = 64;          // max key splits per (b, h): one warp handles ~32 keys
+constexpr int T2S_MAXS = 64;          // max key groups per (b, h)
+constexpr int T2S_BLOCKS_PER_WARP = 4; // 32-key blocks a warp walks before a sequence is split across CTAs
 
 struct T2SLayerW {
     const float* sa_gamma;
@@ -296,6 +297,7 @@ __device__ int t2s_trace_step = -1;
     do {                                                                                          \
         if (blockIdx.x == 0 && threadIdx.x == 0 && step == t2s_trace_step) t2s_trace_buf[id] = clock64(); \
     } while (0)
+__device__ int t2s_dbg_attn_groups = 0;   // debug: force the number of key groups per (b, h) (COVO_T2S_ATTN_GROUPS)
 __device__ int t2s_dbg_no_prefetch = 0;
 __device__ int t2s_dbg_skip_gemv = 0;     // debug: time the kernel without the matrix products (tools/t2s_bench.py)
 
@@ -657,12 +659,12 @@ __device__ __forceinline__ void t2s_attention_stage(const T2SDecArgs& a, int NB,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblocks = (nkeys + 31) / 32;
     const int BH = NB * a.H;
-    // groups: a CTA takes up to 16 blocks (one per warp; a full group costs no more latency than one block and, when it
-    // covers the whole sequence, saves the cross-CTA merge), or up to 32 (two per warp) when that lets all units run in
-    // one round of the grid
-    int ngroups = (nblocks + T2S_WARPS - 1) / T2S_WARPS;
-    if (BH * ngroups > static_cast<int>(gridDim.x)) ngroups = (nblocks + 2 * T2S_WARPS - 1) / (2 * T2S_WARPS);
-    const int bpg = (nblocks + ngroups - 1) / ngroups;                                           // <= 32
+    // groups: one CTA per (b, h) as long as a warp gets at most T2S_BLOCKS_PER_WARP blocks (2048 keys): the result goes
+    // straight to attn[] with an in-smem merge -- no partials, fence, atomic or last-arriver merge through memory; longer
+    // sequences are split into several groups
+    int ngroups = (nblocks + T2S_BLOCKS_PER_WARP * T2S_WARPS - 1) / (T2S_BLOCKS_PER_WARP * T2S_WARPS);
+    if (t2s_dbg_attn_groups > 0) ngroups = min(t2s_dbg_attn_groups, nblocks);
+    const int bpg = (nblocks + ngroups - 1) / ngroups;
     const int units = BH * ngroups;
     constexpr float NEG = -3.402823466e38f;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
