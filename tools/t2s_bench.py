@@ -20,7 +20,7 @@ def main():
     fmts = os.environ.get("T2S_FMTS", "bf16,fp32").split(",")
     batches = [int(b) for b in os.environ.get("T2S_B", "1,2,4,8").split(",")]
     for fmt in fmts:
-        m = B200TextToSemantic(sd, cfg, dev, weight_format=fmt)
+        m = B200TextToSemantic(sd, cfg, dev, weight_format=fmt, sm_limit=int(os.environ.get("T2S_SMS", "0")) or None)
         for B in batches:
             ids = syn.synthetic_text_ids(cfg, B, 200, seed=4, ragged=False).to(dev)
             u = torch.rand(steps, cfg.n_out, B, cfg.n_logits, device=dev)
