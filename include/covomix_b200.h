@@ -73,6 +73,11 @@ size_t covo_flow_workspace_bytes(const covo_flow* h, int B, int N, int n_eval_ti
 int covo_flow_sample(covo_flow* h, const int64_t* ids, const float* cond, const float* y0, float* out, int B, int N,
                      int method, int n_steps, float cond_scale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* torchdiffeq's fixed grid (FixedGridODESolver, options={'step_size': h}, acoustic.py:586-591) is k*h with the last point
+ * snapped to 1, so a step size that does not divide 1 (e.g. 0.3 -> 0, .3, .6, .9, 1) ends on a shorter step.  After this
+ * call covo_flow_sample builds that grid; its n_steps argument must then equal ceil(1/step_size).  0 restores k/n_steps. */
+int covo_flow_set_step_size(covo_flow* h, float step_size);
+
 /* One velocity evaluation  v = CoVoMix.forward_with_cond_scale(x, times=t, ...) (acoustic.py:414-428):
  * x, v f32 [B,N,dim_x].  Used by parity tests and for the "ODE-step ms" metric. */
 int covo_flow_velocity(covo_flow* h, const int64_t* ids, const float* cond, const float* x, float t, float* v, int B,

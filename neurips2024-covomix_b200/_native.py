@@ -24,7 +24,7 @@ EXPORTS = (
     "covo_t2s_create", "covo_t2s_destroy", "covo_t2s_workspace_bytes", "covo_t2s_generate",
     "covo_t2s_launches_per_generate", "covo_t2s_weight_bytes_per_step",
     "covo_mel_create", "covo_mel_destroy", "covo_mel_frames", "covo_mel_forward",
-    "covo_flow_set_sm_limit", "covo_hifigan_set_sm_limit", "covo_t2s_set_sm_limit",
+    "covo_flow_set_sm_limit", "covo_hifigan_set_sm_limit", "covo_t2s_set_sm_limit", "covo_flow_set_step_size",
 )
 
 
@@ -59,6 +59,18 @@ COVO_T2S_IGNORE_EOS = 1
 _lib = None
 
 
+def resolve_device(device):
+    """``torch.device`` with an explicit CUDA ordinal: ``"cuda"`` without an index means the CURRENT device (what
+    ``torch.cuda.set_device(local_rank)`` selected), not GPU 0.  There is no CPU path."""
+    import torch
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("covomix_b200 has no CPU path; device must be a CUDA (sm_100) device")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
@@ -78,6 +90,7 @@ def lib() -> C.CDLL:
     L.covo_flow_sample.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, sz, vp]
     L.covo_flow_velocity.argtypes = [vp, vp, vp, vp, f32, vp, i32, i32, f32, vp, sz, vp]
     L.covo_flow_launches_per_sample.argtypes = [vp, i32, i32, f32]
+    L.covo_flow_set_step_size.argtypes = [vp, f32]
     L.covo_hifigan_create.argtypes = [C.POINTER(HifiganCfg), vp, sz, i32, C.POINTER(vp)]
     L.covo_hifigan_destroy.argtypes = [vp]
     L.covo_hifigan_workspace_bytes.argtypes = [vp, i32, i32]

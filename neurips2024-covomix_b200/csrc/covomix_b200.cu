@@ -100,6 +100,13 @@ size_t covo_flow_workspace_bytes(const covo_flow* h, int B, int N, int n_eval_ti
     return flow_layout(h, p);
 }
 
+int covo_flow_set_step_size(covo_flow* h, float step_size) {
+    if (!h) return fail(COVO_ERR_INVALID, "null handle");
+    if (!(step_size >= 0.f) || step_size > 1.f) return fail(COVO_ERR_INVALID, "step_size=%g out of range (0 = uniform grid, else (0, 1])", step_size);
+    h->step_size = step_size;
+    return COVO_OK;
+}
+
 int covo_flow_launches_per_sample(const covo_flow* h, int method, int n_steps, float cond_scale) {
     if (!h) return 0;
     (void)cond_scale;

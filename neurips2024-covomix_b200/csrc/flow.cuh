@@ -23,6 +23,7 @@ struct FlowPlan {
     // key
     int B = 0, N = 0, method = 0, n_steps = 0, single_eval = 0;
     float cond_scale = 0.f;
+    float step_size = 0.f;         // 0: uniform grid k / n_steps
     void* ws = nullptr;
     // derived
     int two_branch = 1, M = 0, BN = 0, n_t = 0;
@@ -61,6 +62,7 @@ struct covo_flow {
     cudaStream_t capture_stream = nullptr;
     bool use_graph = true;
     bool naive_attn = false;
+    float step_size = 0.f;         // covo_flow_set_step_size: torchdiffeq grid k*h with the last point snapped to 1
 };
 
 namespace covo {
@@ -141,7 +143,8 @@ inline size_t flow_layout(const covo_flow* h, FlowPlan& p) {
 inline void flow_times(FlowPlan& p) {
     // torchdiffeq fixed grid: grid[k] = k*h (+t0 = 0), last point snapped to 1; dt = grid[k+1]-grid[k];
     // midpoint evaluates at grid[k] and grid[k] + dt/2.  All in fp32 like the reference.
-    const float hstep = 1.0f / static_cast<float>(p.n_steps);
+    // (step sizes that do not divide 1, e.g. 0.3, give 0, .3, .6, .9, 1: the last step is shorter.)
+    const float hstep = p.step_size > 0.f ? p.step_size : 1.0f / static_cast<float>(p.n_steps);
     int idx = 0;
     for (int k = 0; k < p.n_steps; ++k) {
         const float t0 = static_cast<float>(k) * hstep;
@@ -378,7 +381,7 @@ inline int flow_enqueue_network(covo_flow* h, FlowPlan& p, int t_idx, cudaStream
 
 inline int flow_enqueue_sample(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
     const covo_flow_cfg& c = h->cfg;
-    const int n_el = p.BN * c.dim_x;
+    const int n_el = p.BN * h->ldx;                 // the element-wise kernels also rewrite the padding columns of xin
     const int eb = ceil_div(n_el, 256);
     COVO_TRY(flow_enqueue_prologue(h, p, st, launches));
     {
@@ -425,7 +428,7 @@ inline int flow_enqueue_sample(covo_flow* h, FlowPlan& p, cudaStream_t st, int* 
 
 inline int flow_enqueue_velocity(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
     const covo_flow_cfg& c = h->cfg;
-    const int n_el = p.BN * c.dim_x;
+    const int n_el = p.BN * h->ldx;                 // the element-wise kernels also rewrite the padding columns of xin
     const int eb = ceil_div(n_el, 256);
     COVO_TRY(flow_enqueue_prologue(h, p, st, launches));
     {
@@ -455,9 +458,13 @@ inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, fl
     if (method != COVO_ODE_EULER && method != COVO_ODE_MIDPOINT) return fail(COVO_ERR_INVALID, "unknown ODE method %d", method);
     const int n_t = single_eval ? 1 : flow_num_times(method, n_steps);
     if (n_steps < 1 || n_t > FLOW_MAX_TIMES) return fail(COVO_ERR_INVALID, "n_steps=%d out of range", n_steps);
+    const float step_size = single_eval ? 0.f : h->step_size;
+    if (step_size > 0.f && n_steps != static_cast<int>(ceilf(1.0f / step_size)))
+        return fail(COVO_ERR_INVALID, "n_steps=%d does not match ceil(1/step_size) = %d (covo_flow_set_step_size(%g))", n_steps,
+                    static_cast<int>(ceilf(1.0f / step_size)), step_size);
     for (FlowPlan* q : h->plans) {
         if (q->B == B && q->N == N && q->method == method && q->n_steps == n_steps && q->cond_scale == cond_scale &&
-            q->single_eval == single_eval && q->ws == ws) {
+            q->single_eval == single_eval && q->ws == ws && q->step_size == step_size) {
             *out = q;
             return COVO_OK;
         }
@@ -469,6 +476,7 @@ inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, fl
     p->n_steps = n_steps;
     p->cond_scale = cond_scale;
     p->single_eval = single_eval;
+    p->step_size = step_size;
     p->ws = ws;
     p->two_branch = (cond_scale != 1.0f) ? 1 : 0;     // acoustic.py:423-424: cond_scale == 1 returns the cond branch only
     p->BN = B * N;
@@ -485,10 +493,9 @@ inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, fl
         delete p;
         return rc;
     }
-    // padding columns of the bf16 operands must be zero (they meet zero weight columns, but 0 * NaN != 0)
-    cudaMemsetAsync(p->a_pc, 0, static_cast<size_t>(p->M) * h->kpc * 2, h->capture_stream);
-    cudaMemsetAsync(p->xin, 0, static_cast<size_t>(p->M) * h->ldx * 2, h->capture_stream);
-    COVO_CK(cudaStreamSynchronize(h->capture_stream));
+    // padding columns of the bf16 operands (a_pc, xin) must be exact zeros (they meet zero weight columns, but
+    // 0 * NaN != 0): embed_input_kernel / state_to_input_kernel / cfg_update_kernel rewrite them on EVERY call, so a
+    // cached plan stays valid when the caller reuses or re-allocates the workspace between calls.
     if (!single_eval && h->use_graph) {
         cudaGraph_t graph = nullptr;
         int launches = 0;

@@ -331,8 +331,7 @@ inline int hifi_get_plan(covo_hifigan* h, int B, int T, void* ws, size_t ws_byte
         delete p;
         return rc;
     }
-    // zero once: padded channels of the mel operand must be exact zeros
-    COVO_CK(cudaMemset(p->mel_tc, 0, static_cast<size_t>(B) * T * h->mel_pad * 2));
+    // padded channels of the mel operand must be exact zeros: mel_to_tc_kernel rewrites them on every call
     if (h->plans.size() >= 8) {
         delete h->plans.front();
         h->plans.erase(h->plans.begin());
@@ -346,7 +345,7 @@ inline int hifi_enqueue(covo_hifigan* h, HifiPlan& p, const float* mel, void* wa
     const covo_hifigan_cfg& c = h->cfg;
     {
         ProfScope ps(PC_ELEMWISE, 0.0, st);
-        dim3 g(ceil_div(p.T, 32), ceil_div(c.num_mels, 32), p.B);
+        dim3 g(ceil_div(p.T, 32), ceil_div(h->mel_pad, 32), p.B);
         mel_to_tc_kernel<<<g, 256, 0, st>>>(mel, p.mel_tc, c.num_mels, p.T, h->mel_pad, h->is_fp16);
         COVO_CK(cudaGetLastError());
     }

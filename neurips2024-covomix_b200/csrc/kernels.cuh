@@ -90,12 +90,17 @@ __global__ void embed_input_kernel(const long long* __restrict__ ids, const floa
     const int src = null_branch ? row - BN : row;
     __nv_bfloat16* o = out + static_cast<size_t>(row) * ldk;
     for (int s = 0; s < S; ++s) {
-        const long long id = null_branch ? null_id : ids[static_cast<size_t>(src) * S + s];
+        long long id = null_branch ? null_id : ids[static_cast<size_t>(src) * S + s];
+        // memory safety only: the host mirror rejects ids outside [0, null_id] like nn.Embedding does (acoustic.py:367-368)
+        if (id < 0 || id > null_id) id = null_id;
         const float* e = table + static_cast<size_t>(id) * demb;
         for (int j = threadIdx.x; j < demb; j += blockDim.x) o[s * demb + j] = __float2bfloat16(e[j]);
     }
     const float* c = null_branch ? null_cond : cond + static_cast<size_t>(src) * dim_in;
     for (int j = threadIdx.x; j < dim_in; j += blockDim.x) o[S * demb + j] = __float2bfloat16(c[j]);
+    // padding columns are rewritten on every call: they meet zero weight columns, but 0 * NaN != 0 and the
+    // workspace belongs to the caller between calls
+    for (int j = S * demb + dim_in + threadIdx.x; j < ldk; j += blockDim.x) o[j] = __float2bfloat16(0.f);
 }
 
 // ConvPositionEmbed + residual (acoustic.py:153-161, :508): x = gelu(dwconv31(h) + b) + h over time, per channel.
@@ -180,9 +185,17 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 __global__ void cfg_update_kernel(const float* __restrict__ v_pred /*[2*BN or BN, dx]*/, const float* x_base,
                                   float* x_out, float* __restrict__ v_out, __nv_bfloat16* __restrict__ xin, int BN,
                                   int dx, int ldx, float s, float coef, int two_branch) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= BN * dx) return;
-    const int r = idx / dx, c = idx % dx;
+    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= BN * ldx) return;
+    const int r = gidx / ldx, c = gidx % ldx;
+    if (c >= dx) {                                   // padding columns of the network input: exact zeros, every call
+        if (xin != nullptr) {
+            xin[static_cast<size_t>(r) * ldx + c] = __float2bfloat16(0.f);
+            if (two_branch) xin[static_cast<size_t>(BN + r) * ldx + c] = __float2bfloat16(0.f);
+        }
+        return;
+    }
+    const int idx = r * dx + c;
     float v = v_pred[idx];
     if (two_branch) v = (1.0f + s) * v - s * v_pred[static_cast<size_t>(BN) * dx + idx];
     if (v_out != nullptr) v_out[idx] = v;
@@ -199,10 +212,10 @@ __global__ void cfg_update_kernel(const float* __restrict__ v_pred /*[2*BN or BN
 // x (fp32 [BN, dx]) -> bf16 network input rows for both CFG branches.
 __global__ void state_to_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xin, int BN, int dx,
                                       int ldx, int two_branch) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= BN * dx) return;
-    const int r = idx / dx, c = idx % dx;
-    const __nv_bfloat16 hb = __float2bfloat16(x[idx]);
+    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= BN * ldx) return;
+    const int r = gidx / ldx, c = gidx % ldx;
+    const __nv_bfloat16 hb = __float2bfloat16(c < dx ? x[r * dx + c] : 0.f);   // padding columns: exact zeros, every call
     xin[static_cast<size_t>(r) * ldx + c] = hb;
     if (two_branch) xin[static_cast<size_t>(BN + r) * ldx + c] = hb;
 }
@@ -235,7 +248,8 @@ __global__ void mel_to_tc_kernel(const float* __restrict__ mel, uint16_t* __rest
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int t = t0 + i, c = c0 + tx;
-        if (t < T && c < C) out[(static_cast<size_t>(b) * T + t) * ldc + c] = to_h(tile[tx][i], is_fp16);
+        // channels [C, ldc) are written as zeros on every call (the workspace belongs to the caller between calls)
+        if (t < T && c < ldc) out[(static_cast<size_t>(b) * T + t) * ldc + c] = to_h(tile[tx][i], is_fp16);
     }
 }
 

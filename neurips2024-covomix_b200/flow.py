@@ -23,13 +23,15 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 
 class B200FlowSampler:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[FlowConfig] = None, device="cuda:0",
-                 torchdiffeq_ode_method: str = "midpoint", ode_step_size: float = 0.0625, sm_limit: Optional[int] = None):
+                 torchdiffeq_ode_method: str = "midpoint", ode_step_size: float = 0.0625, sm_limit: Optional[int] = None,
+                 validate_ids: bool = True):
         self.cfg = cfg if cfg is not None else flow_config_from_state_dict(state_dict)
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("covomix_b200 has no CPU path; device must be a CUDA (sm_100) device")
+        self.device = nat.resolve_device(device)
         self.method = torchdiffeq_ode_method
         self.step_size = float(ode_step_size)
+        if not 0.0 < self.step_size <= 1.0:
+            raise ValueError(f"ode_step_size must be in (0, 1], got {ode_step_size}")
+        self.validate_ids = bool(validate_ids)     # one min/max reduction + host read per call (the reference's IndexError)
         c = self.cfg
         ccfg = nat.FlowCfg(dim=c.dim, depth=c.depth, heads=c.heads, dim_head=c.dim_head, dim_in=c.dim_in, dim_x=c.dim_x,
                            n_streams=c.n_streams, num_phoneme_tokens=c.num_phoneme_tokens,
@@ -38,7 +40,10 @@ class B200FlowSampler:
         self._h = C.c_void_p()
         L = nat.lib()
         nat.check(L.covo_flow_create(C.byref(ccfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
-                                     self.device.index or 0, C.byref(self._h)), "covo_flow_create")
+                                     self.device.index, C.byref(self._h)), "covo_flow_create")
+        # torchdiffeq's grid is k*h with the last point snapped to 1 (a step size that does not divide 1 ends on a shorter
+        # step); the library builds exactly that grid from the step size
+        nat.check(L.covo_flow_set_step_size(self._h, self.step_size), "covo_flow_set_step_size")
         if sm_limit:       # persistent kernels of this handle use at most sm_limit SMs (stage overlap, see include/covomix_b200.h)
             nat.check(L.covo_flow_set_sm_limit(self._h, int(sm_limit)), "covo_flow_set_sm_limit")
         self._ws: Dict[tuple, torch.Tensor] = {}
@@ -77,10 +82,17 @@ class B200FlowSampler:
             raise ValueError(f"phoneme_ids must be {want}, got {tuple(phoneme_ids.shape)}")
         ids = phoneme_ids.to(device=self.device, dtype=torch.int64).contiguous()
         cond = cond.to(device=self.device, dtype=torch.float32).contiguous()
+        if self.validate_ids and ids.numel():
+            # nn.Embedding(num_phoneme_tokens + 1, ...) raises on ids outside the table (acoustic.py:367-368, :496-500)
+            lo, hi = (int(v) for v in torch.stack((ids.min(), ids.max())).tolist())
+            if lo < 0 or hi > c.num_phoneme_tokens:
+                raise IndexError(f"phoneme_ids out of range: [{lo}, {hi}] not within [0, {c.num_phoneme_tokens}]")
         return ids, cond, B, N
 
     def n_steps(self) -> int:
-        return int(math.ceil(1.0 / self.step_size))
+        """Number of solver steps of torchdiffeq's fixed grid: ceil(1/h) evaluated in fp32 like the library does."""
+        one, h = torch.tensor(1.0), torch.tensor(self.step_size, dtype=torch.float32)
+        return int(math.ceil(float(one / h)))
 
     # --------------------------------------------------------------------------------
     @torch.inference_mode()

@@ -46,9 +46,7 @@ class B200MelSpectrogram:
     dicts (generate_mel.py:46-58)."""
 
     def __init__(self, device="cuda:0"):
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("covomix_b200 has no CPU path; device must be a CUDA (sm_100) device")
+        self.device = nat.resolve_device(device)
         self._handles: Dict[Tuple, C.c_void_p] = {}
 
     def _handle(self, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax):
@@ -60,7 +58,7 @@ class B200MelSpectrogram:
             cfg = nat.MelCfg(n_fft=n_fft, hop_size=hop_size, win_size=win_size, num_mels=num_mels)
             h = C.c_void_p()
             nat.check(nat.lib().covo_mel_create(C.byref(cfg), window.ctypes.data_as(C.c_void_p),
-                                                basis.ctypes.data_as(C.c_void_p), self.device.index or 0, C.byref(h)),
+                                                basis.ctypes.data_as(C.c_void_p), self.device.index, C.byref(h)),
                       "covo_mel_create")
             self._handles[key] = h
         return h

@@ -67,6 +67,16 @@ class BlobBuilder:
         return blob
 
 
+def blob_entry_names(blob: np.ndarray) -> List[str]:
+    """Names of the tensors in a packed blob (the table the C side binds by name, csrc/common.cuh ``Weights``)."""
+    n = struct.unpack("<I", bytes(blob[8:12]))[0]
+    out = []
+    for i in range(n):
+        rec = _ENTRY.unpack(bytes(blob[16 + i * _ENTRY.size:16 + (i + 1) * _ENTRY.size]))
+        out.append(rec[0].split(b"\0", 1)[0].decode())
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # flow-matching velocity net
 # --------------------------------------------------------------------------------------

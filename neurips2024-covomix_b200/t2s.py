@@ -64,9 +64,7 @@ class B200TextToSemantic:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[T2SConfig] = None, device="cuda:0",
                  weight_format: str = "bf16", sm_limit: Optional[int] = None):
         self.cfg = cfg if cfg is not None else t2s_config_from_state_dict(state_dict)
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("covomix_b200 has no CPU path; device must be a CUDA (sm_100) device")
+        self.device = nat.resolve_device(device)
         if weight_format not in ("bf16", "fp32"):
             raise ValueError(weight_format)
         c = self.cfg
@@ -78,7 +76,7 @@ class B200TextToSemantic:
         blob = pack_t2s_weights(state_dict, c, weight_format)
         self._h = C.c_void_p()
         nat.check(nat.lib().covo_t2s_create(C.byref(ccfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
-                                            self.device.index or 0, C.byref(self._h)), "covo_t2s_create")
+                                            self.device.index, C.byref(self._h)), "covo_t2s_create")
         if sm_limit:       # the decode kernel's grid: sm_limit CTAs instead of one per SM (stage overlap)
             nat.check(nat.lib().covo_t2s_set_sm_limit(self._h, int(sm_limit)), "covo_t2s_set_sm_limit")
         self._ws: Dict[tuple, torch.Tensor] = {}

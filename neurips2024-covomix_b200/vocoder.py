@@ -1,6 +1,6 @@
 """Host-side mirror of the HiFi-GAN ``Generator`` (hifi-gan/models.py:75-125 ==
 covomix/vocoder/models.py) backed by libcovomix_b200.so.  ``gen(mel)`` takes the reference's input
-([80, T] or [B, 80, T] fp32) and returns the reference's output shape ([1, 1, L] / [B, 1, L] fp32,
+([80, T] or [B, 80, T] fp32) and returns the reference's output shape ([1, L] / [B, 1, L] fp32,
 L = 160*T + 32 for config_covomix.json); ``eval()`` / ``remove_weight_norm()`` / ``to()`` exist so the
 generation scripts' load sequence (monologue_generation.py:382-386) runs unchanged.
 """
@@ -24,9 +24,7 @@ class B200Generator:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: HifiganConfig = HIFIGAN_COVOMIX, device="cuda:0",
                  h_format: str = "fp16", sm_limit=None):
         self.h = cfg
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("covomix_b200 has no CPU path; device must be a CUDA (sm_100) device")
+        self.device = nat.resolve_device(device)
         nk = len(cfg.resblock_kernel_sizes)
         nd = len(cfg.resblock_dilation_sizes[0])
         ccfg = nat.HifiganCfg()
@@ -47,7 +45,7 @@ class B200Generator:
         blob = pack_hifigan_weights(state_dict, cfg, h_format)
         self._h = C.c_void_p()
         nat.check(nat.lib().covo_hifigan_create(C.byref(ccfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
-                                                self.device.index or 0, C.byref(self._h)), "covo_hifigan_create")
+                                                self.device.index, C.byref(self._h)), "covo_hifigan_create")
         if sm_limit:
             nat.check(nat.lib().covo_hifigan_set_sm_limit(self._h, int(sm_limit)), "covo_hifigan_set_sm_limit")
         self._ws: Dict[tuple, torch.Tensor] = {}
@@ -109,13 +107,18 @@ class B200Generator:
 
     @torch.inference_mode()
     def forward(self, mel: torch.Tensor, out_dtype: str = "f32") -> torch.Tensor:
-        x = mel if mel.ndim == 3 else mel[None]
+        unbatched = mel.ndim == 2
+        x = mel[None] if unbatched else mel
         if x.ndim != 3 or x.shape[1] != self.h.num_mels:
             raise ValueError(f"mel must be [{self.h.num_mels}, T] or [B, {self.h.num_mels}, T], got {tuple(mel.shape)}")
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         B, _, T = x.shape
         code, tdt = {"f32": (nat.COVO_WAV_F32, torch.float32), "f16": (nat.COVO_WAV_F16, torch.float16),
                      "i16": (nat.COVO_WAV_I16, torch.int16)}[out_dtype]
+        if unbatched:
+            # Generator.forward on [80, T]: Conv1d treats it as an unbatched [C, T] input, so the result is [1, L]
+            # (hifi-gan/models.py:100-116) -- not [1, 1, L]
+            return self.forward(x, out_dtype)[0]
         if B * T <= self.MAX_FRAMES_PER_CALL:
             return self._forward_one(x, code, tdt)
         hop, halo = self.h.hop, self.HALO

@@ -241,8 +241,10 @@ def resblock2(sd, prefix: str, x: Tensor, k: int, dils: Sequence[int]) -> Tensor
 @torch.inference_mode()
 def hifigan_forward(sd, cfg, mel: Tensor) -> Tensor:
     """Generator.forward (models.py:100-116) on weights after remove_weight_norm.
-    mel [B,80,T] or [80,T] -> [B|1, 1, hop*T + 32] for config_covomix.json."""
-    x = mel if mel.ndim == 3 else mel[None]
+    mel [B,80,T] -> [B, 1, hop*T + 32]; unbatched [80,T] -> [1, hop*T + 32] (Conv1d's unbatched convention, which is
+    what the reference module returns) for config_covomix.json."""
+    unbatched = mel.ndim == 2
+    x = mel[None] if unbatched else mel
     x = F.conv1d(x, sd["conv_pre.weight"], sd["conv_pre.bias"], padding=3)
     nk = len(cfg.resblock_kernel_sizes)
     rb = resblock1 if cfg.resblock == "1" else resblock2
@@ -256,7 +258,8 @@ def hifigan_forward(sd, cfg, mel: Tensor) -> Tensor:
         x = xs / nk
     x = F.leaky_relu(x)                                   # default slope 0.01 (models.py:112)
     x = F.conv1d(x, sd["conv_post.weight"], sd["conv_post.bias"], padding=3)
-    return torch.tanh(x)
+    x = torch.tanh(x)
+    return x[0] if unbatched else x
 
 
 def wav_to_int16(wav: Tensor):

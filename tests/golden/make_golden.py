@@ -92,6 +92,25 @@ def main():
         print(name, "v", v.shape, float(v.std()), "mel", mel.shape, float(mel.std()))
         del wrapper, sd
 
+    # multi-tile cases (round 2): B = 2, N = 300 -> three 128-key tiles and two query tiles per (sequence, head) inside
+    # the network, so the attention tiling is pinned to the reference module (acoustic.py:430-521), not only to the oracle
+    for name, cfg, B, N in (("vosingle_n300", syn.VOSINGLE, 2, 300), ("vomix_n300", syn.VOMIX, 2, 300)):
+        sd = syn.synthetic_flow_state_dict(cfg, seed=1234)
+        wrapper = ref_flow(cfg, sd)
+        ids, cond, y0, mask = syn.synthetic_flow_inputs(cfg, B, N, prompt=60, seed=31)
+        t = torch.tensor(0.59375)
+        v = wrapper.CoVoMix.forward_with_cond_scale(y0, times=t, phoneme_ids=ids, cond=cond, cond_scale=0.7)
+        torch.manual_seed(78)
+        y0_s = torch.randn_like(cond if not cfg.twocondition_oneoutput else cond[:, :, :80])
+        torch.manual_seed(78)
+        mel = wrapper.sample(phoneme_ids=ids, cond=cond, mask=mask, cond_scale=0.7)
+        # y0 of sample() is the torch.manual_seed(78) CPU draw; tests replay it instead of storing it
+        np.savez_compressed(os.path.join(HERE, f"flow_{name}.npz"),
+                            B=B, N=N, prompt=60, weight_seed=1234, input_seed=31, t=0.59375, cond_scale=0.7, y0_seed=78,
+                            v_cfg=v.numpy(), mel=mel.numpy())
+        print(name, "v", v.shape, float(v.std()), "mel", mel.shape, float(mel.std()))
+        del wrapper, sd
+
     hcfg = syn.HIFIGAN_COVOMIX
     sd = syn.synthetic_hifigan_state_dict(hcfg, seed=1234)
     gen = ref_generator(hcfg, sd)

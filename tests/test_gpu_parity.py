@@ -21,6 +21,20 @@ pytestmark = pytest.mark.gpu
 P = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)
 
 
+def record(what, **numbers):
+    """Measured parity numbers -> stdout and gpurun_out/parity_numbers.jsonl (quoted in DESIGN.md section 2)."""
+    import json
+    line = {"what": what, **{k: float(f"{v:.4g}") for k, v in numbers.items()}}
+    print("PARITY", json.dumps(line))
+    out = os.path.join(os.path.dirname(GOLDEN), os.pardir, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_numbers.jsonl"), "a") as f:
+            f.write(json.dumps(line) + "\n")
+    except OSError:
+        pass
+
+
 def rel_l2(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return float((a - b).norm() / b.norm())
@@ -118,6 +132,121 @@ def test_sample_matches_reference(dev, name, vosingle, vomix):
     assert torch.equal(mel, mel2)
 
 
+# ------------------------------------------------------------------------------------------ multi-tile goldens (N = 300)
+@pytest.mark.parametrize("name", ["vosingle_n300", "vomix_n300"])
+def test_multi_tile_matches_reference(dev, name, vosingle, vomix):
+    """B = 2, N = 300 vectors of the REAL reference module (tests/golden/make_golden.py): three 128-key tiles and two
+    query tiles per (sequence, head) inside the network -- velocity and the sampled mel (midpoint, 32 NFE)."""
+    sd, smp = vosingle if name.startswith("vosingle") else vomix
+    g = np.load(os.path.join(GOLDEN, f"flow_{name}.npz"))
+    ids, cond, y0, mask = syn.synthetic_flow_inputs(smp.cfg, int(g["B"]), int(g["N"]), prompt=int(g["prompt"]),
+                                                    seed=int(g["input_seed"]))
+    v = smp.velocity(y0.to(dev), times=float(g["t"]), phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+    ref = torch.from_numpy(g["v_cfg"])
+    r, mx = rel_l2(v, ref), float((v.cpu() - ref).abs().max()) / float(ref.std())
+    record(f"velocity {name} (reference golden)", rel_l2=r, max_abs_over_sigma=mx)
+    assert r < 1e-2 and mx < 5e-2
+    torch.manual_seed(int(g["y0_seed"]))
+    y0_s = torch.randn_like(cond if smp.cfg.n_streams == 1 else cond[:, :, :80])       # the draw sample() made in the reference
+    mel = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), mask=mask.to(dev), cond_scale=0.7, y0=y0_s.to(dev))
+    ref = torch.from_numpy(g["mel"])
+    r, ma = rel_l2(mel, ref), float((mel.cpu() - ref).abs().mean())
+    record(f"sample {name}, midpoint 32 NFE (reference golden)", rel_l2=r, mean_abs=ma)
+    assert r < 3e-2 and ma < 0.05
+
+
+# ------------------------------------------------------------------------------------------ BASELINE shapes vs the oracle
+@pytest.mark.parametrize("name,N", [("vosingle", 650), ("vomix", 1650)])
+def test_velocity_at_baseline_shapes_vs_oracle(dev, orc, name, N, vosingle, vomix):
+    """One CFG velocity evaluation at the C2 shape (VoSingle, B = 1, N = 650) and at C3's per-item shape (VoMix, B = 1,
+    N = 1650: 13 key tiles, 7 query tiles) against the fp32 oracle run in-test.  SURVEY 8d tolerances."""
+    sd, smp = vosingle if name == "vosingle" else vomix
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(smp.cfg, 1, N, prompt=150, seed=30)
+    v = smp.velocity(y0.to(dev), times=0.40625, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+    with torch.inference_mode():
+        ref = orc.velocity_cfg(sd, smp.cfg, y0, ids, cond, torch.tensor(0.40625), 0.7)
+    r, mx = rel_l2(v, ref), float((v.cpu() - ref).abs().max()) / float(ref.std())
+    record(f"velocity {name} B=1 N={N} (oracle)", rel_l2=r, max_abs_over_sigma=mx)
+    assert r < 1e-2 and mx < 5e-2
+
+
+def test_c2_full_sample_vs_oracle(dev, orc, vosingle):
+    """BASELINE configs[1] end to end: VoSingle, 32 Euler steps, N = 650 (10 s + 3 s prompt), B = 1, against the oracle's
+    own 32-step integration (~40 s of CPU)."""
+    from covomix_b200.flow import B200FlowSampler
+    sd, _ = vosingle
+    smp = B200FlowSampler(sd, syn.VOSINGLE, dev, torchdiffeq_ode_method="euler", ode_step_size=1 / 32)
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, 1, 650, prompt=150, seed=30)
+    mel = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+    with torch.inference_mode():
+        ref = orc.flow_sample(sd, syn.VOSINGLE, ids, cond, y0, cond_scale=0.7, method="euler", step_size=1 / 32)
+    r, ma = rel_l2(mel, ref), float((mel.cpu() - ref).abs().mean())
+    record("sample C2 (VoSingle, 32 Euler steps, N=650) vs oracle", rel_l2=r, mean_abs=ma)
+    assert r < 3e-2 and ma < 0.05
+    smp.close()
+
+
+def test_vomix_64_euler_steps_vs_oracle(dev, orc, vomix):
+    """Error growth over C3's 64 NFE: VoMix, 64 Euler steps, N = 400 (4 key tiles), B = 1, against the oracle."""
+    from covomix_b200.flow import B200FlowSampler
+    sd, _ = vomix
+    smp = B200FlowSampler(sd, syn.VOMIX, dev, torchdiffeq_ode_method="euler", ode_step_size=1 / 64)
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOMIX, 1, 400, prompt=100, seed=33)
+    mel = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+    with torch.inference_mode():
+        ref = orc.flow_sample(sd, syn.VOMIX, ids, cond, y0, cond_scale=0.7, method="euler", step_size=1 / 64)
+    r, ma = rel_l2(mel, ref), float((mel.cpu() - ref).abs().mean())
+    record("sample VoMix, 64 Euler steps, N=400 vs oracle", rel_l2=r, mean_abs=ma)
+    assert r < 3e-2 and ma < 0.05
+    smp.close()
+
+
+def test_step_size_not_dividing_one(dev, orc, vosingle):
+    """torchdiffeq's grid for h = 0.3 is 0, .3, .6, .9, 1 (last step shorter), not k/4."""
+    from covomix_b200.flow import B200FlowSampler
+    sd, _ = vosingle
+    smp = B200FlowSampler(sd, syn.VOSINGLE, dev, torchdiffeq_ode_method="midpoint", ode_step_size=0.3)
+    assert smp.n_steps() == 4
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, 1, 40, prompt=8, seed=5)
+    mel = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+    with torch.inference_mode():
+        ref = orc.flow_sample(sd, syn.VOSINGLE, ids, cond, y0, cond_scale=0.7, method="midpoint", step_size=0.3)
+        uniform = orc.flow_sample(sd, syn.VOSINGLE, ids, cond, y0, cond_scale=0.7, method="midpoint", step_size=0.25)
+    assert rel_l2(mel, ref) < 1e-2 < rel_l2(uniform, ref)     # the uniform grid is measurably a different answer
+    smp.close()
+
+
+def test_reused_workspace_with_garbage_padding(dev, vosingle, vocoder):
+    """a cached plan must not rely on padding columns zeroed at plan-build time -- fill the (library-cached)
+    workspaces with NaN bit patterns between two calls of the same shape."""
+    _, smp = vosingle
+    _, gen = vocoder
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, 1, 72, prompt=8, seed=6)
+    a = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+    va = smp.velocity(y0.to(dev), times=0.5, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+    mel = syn.synthetic_logmel(torch.Generator().manual_seed(3), 2, 80, 40).to(dev)
+    wa = gen(mel)
+    torch.cuda.synchronize()
+    for ws in list(smp._ws.values()) + list(gen._ws.values()):
+        ws.fill_(0xFF)
+    b = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+    vb = smp.velocity(y0.to(dev), times=0.5, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+    wb = gen(mel)
+    assert torch.equal(a, b) and torch.equal(va, vb) and torch.equal(wa, wb)
+
+
+def test_out_of_range_ids_raise(dev, vosingle):
+    _, smp = vosingle
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, 1, 16, prompt=4)
+    bad = ids.clone()
+    bad[0, 3] = 503                     # the table has 503 rows (502 = null id): nn.Embedding raises IndexError
+    with pytest.raises(IndexError):
+        smp.sample(phoneme_ids=bad.to(dev), cond=cond.to(dev), y0=y0.to(dev))
+    bad[0, 3] = -1
+    with pytest.raises(IndexError):
+        smp.sample(phoneme_ids=bad.to(dev), cond=cond.to(dev), y0=y0.to(dev))
+
+
 @pytest.mark.parametrize("N", [1, 31, 130])
 def test_euler_sample_vs_oracle_ragged_lengths(dev, orc, vosingle, N):
     from covomix_b200.flow import B200FlowSampler
@@ -175,8 +304,8 @@ def test_hifigan_matches_reference(dev, vocoder):
     for mel, key in zip(mels, ("wav_c1", "wav_unbatched", "wav_batch")):
         wav = gen(mel.to(dev))
         ref = torch.from_numpy(g[key])
-        assert wav.numel() == ref.numel() and wav.shape[-1] == 160 * mel.shape[-1] + 32
-        assert wav.shape == (mel.shape[0] if mel.ndim == 3 else 1, 1, ref.shape[-1])
+        assert wav.shape[-1] == 160 * mel.shape[-1] + 32
+        assert wav.shape == ref.shape               # reference shapes: [B, 1, L], and [1, L] for the unbatched [80, T] input
         assert rel_l2(wav.reshape(-1), ref.reshape(-1)) < 2e-3
         # mel_decode_to_wav semantics (x32768 -> int16): fused i16 output == host-side cast of our own f32 output
         i16 = gen(mel.to(dev), out_dtype="i16").cpu().numpy().reshape(-1)

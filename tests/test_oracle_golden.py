@@ -32,7 +32,18 @@ def test_velocity_matches_reference(name, cfg):
     assert rel_l2(v_cfg, g["v_cfg"]) < 1e-5
 
 
-@pytest.mark.parametrize("name,cfg", [("vosingle", syn.VOSINGLE)])
+@pytest.mark.parametrize("name,cfg", [("vosingle_n300", syn.VOSINGLE), ("vomix_n300", syn.VOMIX)])
+def test_velocity_matches_reference_multi_tile(name, cfg):
+    """B = 2, N = 300 vectors from the real reference module (three key tiles / two query tiles for the CUDA kernel)."""
+    g = np.load(os.path.join(GOLDEN, f"flow_{name}.npz"))
+    sd = syn.synthetic_flow_state_dict(cfg, seed=int(g["weight_seed"]))
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(cfg, int(g["B"]), int(g["N"]), prompt=int(g["prompt"]),
+                                                 seed=int(g["input_seed"]))
+    v = orc.velocity_cfg(sd, cfg, y0, ids, cond, torch.tensor(float(g["t"])), float(g["cond_scale"]))
+    assert rel_l2(v, g["v_cfg"]) < 1e-5
+
+
+@pytest.mark.parametrize("name,cfg", [("vosingle", syn.VOSINGLE), ("vomix", syn.VOMIX)])
 def test_sample_matches_reference(name, cfg):
     g = np.load(os.path.join(GOLDEN, f"flow_{name}.npz"))
     sd = syn.synthetic_flow_state_dict(cfg, seed=int(g["weight_seed"]))
@@ -53,7 +64,7 @@ def test_hifigan_matches_reference():
     for mel, key in ((mel_c1, "wav_c1"), (mel_u, "wav_unbatched"), (mel_b, "wav_batch")):
         wav = orc.hifigan_forward(sd, cfg, mel)
         ref = g[key]
-        assert wav.numel() == ref.size
+        assert tuple(wav.shape) == ref.shape        # [1, L] for the unbatched [80, T] input, [B, 1, L] otherwise
         assert wav.shape[-1] == cfg.out_len(mel.shape[-1]) == 160 * mel.shape[-1] + 32
         assert rel_l2(wav.reshape(-1), ref.reshape(-1)) < 1e-5
 
