@@ -3,23 +3,29 @@
 // Replaces Attend.forward's einsum/softmax/einsum (covomix/covomix_model/attend.py:110-124), which
 // materialises the [B,H,N,N] fp32 score tensor in HBM; here scores never leave the SM.
 //
-// Persistent: grid = min(#work items, #SMs); a work item = (sequence b, head h, 256-query tile), and the TMA / MMA /
-// softmax pipelines run straight across item boundaries (Q is double-buffered), so TMEM allocation, barrier set-up,
-// the first Q/K loads and the output stores of one item hide behind the neighbouring items' work.
-// A work item = two 128-query groups A and B that share every
-// K/V tile and ping-pong on the tensor pipe: while the softmax warps of one group work on S_j, the
-// MMAs of the other group run.  Q/K/V tiles are TMA-loaded straight out of the to_qkv GEMM's
-// [B*N, 3*H*64] bf16 output (3-D tensor map: column, position, sequence; rows past the end of a
-// sequence are zero-filled by TMA and masked to -inf in the softmax).
-//   warp 0      : TMA producer (both Q tiles once, then a 2-stage ring of K and V tiles of 128 keys)
+// Persistent: grid = min(#work items, #SMs).  A sequence is cut into 128-query groups; a work item is a PAIR of groups
+// A and B of one (sequence, head) that share every K/V tile (or the single left-over group when the group count is odd;
+// pairs are dealt first so the short items fill the tail of the schedule).  The TMA / MMA / softmax pipelines run
+// straight across item boundaries (Q is double-buffered).  Q/K/V tiles are TMA-loaded straight out of the to_qkv
+// GEMM's [B*N, 3*H*64] bf16 output (3-D tensor map: column, position, sequence; rows past the end of a sequence are
+// zero-filled by TMA and masked to -inf in the softmax).
+//   warp 0      : TMA producer (Q tiles of the next item, a 3-stage ring of K tiles and a 4-stage ring of V tiles)
 //   warp 1      : tcgen05.mma issuer:  S_g = Q_g K_j^T (M128 x N128 x K64, K-major operands, into TMEM),
-//                 O_g = P_g V_j (M128 x N64 x K128, A = P from TMEM, B = V MN-major, into TMEM);
-//                 S_g(j) is issued before P_g(j-1) V_{j-1} so the pipe always has work queued
-//   warps 4-7   : softmax group A, warps 8-11: group B; one query row per thread (TMEM lane == row, so
-//                 row max / row sum need no shuffles): S_j from TMEM into registers (buffer released at
-//                 once) -> running max, exp2, row sum -> P_j as bf16 pairs into TMEM (the A
-//                 operand of the PV MMA; written with tcgen05.st, so no smem round trip and no proxy fence) -> O_{j-1} from TMEM, rescale-and-accumulate in registers.
-// Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 56, softmax warpgroups 224; the pool is exactly what warpgroup 0 releases).
+//                 O_g += P_g V_j (M128 x N64 x K128, A = P from TMEM, B = V MN-major); O ACCUMULATES IN TMEM over the
+//                 key tiles of an item.  Issue order per step u:  S_A(u), PV_B(u-2), S_B(u), PV_A(u-1) -- the order in
+//                 which the operands become ready when group B runs half a tile behind group A, so that one group's
+//                 exponentials (MUFU-bound) overlap the other group's TMEM traffic, row max and barrier latencies.
+//   warps 4-7   : softmax group A, warps 8-11: group B; one query row per thread (TMEM lane == row, so row max / row
+//                 sum need no shuffles): S_j from TMEM into registers (buffer released at once) -> running max ->
+//                 p = exp2((s - m) / 8 * log2 e) -> P_j as bf16 pairs into TMEM (tcgen05.st, the A operand of the PV MMA).
+//                 The running max is only raised (and O, l rescaled in TMEM by the same thread) when it moves by more than
+//                 2^8 for some row of the warp -- the result is the exact softmax either way, P merely carries a
+//                 common factor <= 256 -- so the common per-tile path touches neither O nor a correction factor.
+//                 Arithmetic: packed fp32 pairs (FFMA2 / FADD2); a fixed fraction of the exponentials is evaluated on
+//                 the FMA pipe (Cody-Waite split + degree-3 minimax, |rel err| < 7.5e-5, far below the bf16 rounding
+//                 of P) because MUFU.EX2 (8 cycles per warp instruction per sub-partition) is the binding unit:
+//                 tools/micro/softmax_loop.cu, profiles/r02_softmax_loop_micro.txt.
+// Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 56, softmax warpgroups 224; the pool of setmaxnreg.inc is exactly what warpgroup 0 releases)..
 #pragma once
 #include "ptx.cuh"
 
@@ -28,19 +34,22 @@ namespace covo {
 // Optional clock64 timeline of the softmax loop (tools/micro/attn_trace.cu); compiled out in the library.
 #ifdef ATT_TRACE
 __device__ long long g_trace[4096];
-#define TR(slot) do { if (blockIdx.x == 0 && lane == 0 && it >= 40 && it < 44) g_trace[(warp) * 256 + (it - 40) * 16 + (slot)] = clock64(); } while (0)
+#define TR(slot) do { if (blockIdx.x == 0 && lane == 0 && itg >= 40 && itg < 44) g_trace[(warp) * 256 + (itg - 40) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define TR(slot)
 #endif
 
-constexpr int ATT_BM = 256;      // queries per CTA (two groups of 128)
+constexpr int ATT_BM = 256;      // queries per pair item (two groups of 128)
+constexpr int ATT_BG = 128;      // queries per group
 constexpr int ATT_BN = 128;      // keys per iteration
 constexpr int ATT_D = 64;        // dim_head
+constexpr int ATT_KS = 3;        // K ring stages
+constexpr int ATT_VS = 4;        // V ring stages (V_j is still needed two steps after K_j)
 constexpr int ATT_THREADS = 384; // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1, 2: softmax A, B
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                 // 16 KB: one [128 x 64] bf16 tile
-constexpr int ATT_SMEM_BYTES = 4 * ATT_TILE_BYTES /*Q x2 buffers*/ + 2 * ATT_TILE_BYTES /*K*/ + 2 * ATT_TILE_BYTES /*V*/ +
-                               256 + 1024;
+constexpr int ATT_SMEM_BYTES = (4 + ATT_KS + ATT_VS) * ATT_TILE_BYTES + 512 + 1024;
 constexpr int ATT_TMEM_COLS = 512;                           // S: 2 x 128, O: 2 x 64, P (bf16 pairs): 2 x 64
+constexpr float ATT_RESCALE_LOG2 = 8.0f;                     // raise the running max only when it moves by more than 2^8
 
 struct AttnArgs {
     CUtensorMap tmQKV;     // (col, pos, seq) over [Bt, N, 3*inner] bf16, box (64, 128, 1), SWIZZLE_128B
@@ -48,63 +57,135 @@ struct AttnArgs {
     int N;                 // sequence length
     int heads;
     int inner;             // heads * 64
-    float scale_log2e;     // dim_head^-0.5 * log2(e)
-    int n_qt;              // query tiles per (sequence, head) = ceil(N / 256)
-    int n_items;           // n_qt * heads * sequences
+    int n_pairs;           // pair items per (sequence, head) = ceil(N / 128) / 2
+    int n_pair_items;      // n_pairs * heads * sequences
+    int n_items;           // + one single-group item per (sequence, head) when ceil(N / 128) is odd
+    int stagger;           // != 0: exponential token between the two query groups (anti-phase); 0: free running
 };
+
+inline void attn_fill_items(AttnArgs& a, int sequences) {
+    const int groups = (a.N + ATT_BG - 1) / ATT_BG;
+    a.n_pairs = groups / 2;
+    a.n_pair_items = a.n_pairs * a.heads * sequences;
+    a.n_items = a.n_pair_items + (groups & 1) * a.heads * sequences;
+}
+
+struct AttnItem {
+    int seq, head, q0, two;
+};
+__device__ __forceinline__ AttnItem attn_decode(const AttnArgs& args, int w) {
+    AttnItem it;
+    int r;
+    if (w < args.n_pair_items) {
+        it.q0 = (w % args.n_pairs) * ATT_BM;
+        r = w / args.n_pairs;
+        it.two = 1;
+    } else {
+        it.q0 = args.n_pairs * ATT_BM;
+        r = w - args.n_pair_items;
+        it.two = 0;
+    }
+    it.head = r % args.heads;
+    it.seq = r / args.heads;
+    return it;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
 __device__ __forceinline__ float fmax3(float a, float b, float c) {   // sm_100 three-input max: one FMNMX3 instead of two FMNMX
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): two lanes of one 64-bit register pair per instruction
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// 2^x for a pair on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x) through the 1.5 * 2^23 trick, 2^f from a
+// degree-3 minimax polynomial on [-0.5, 0.5] (max relative error 7.5e-5), 2^n added into the exponent field.
+// x is clamped at -125 (the result is then ~2e-38 instead of 0 -- masked keys carry -inf).  x <= ~8 by construction.
+__device__ __forceinline__ void exp2_fma2(float& p0, float& p1, float x0, float x1) {
+    constexpr float MAGIC = 12582912.f;
+    x0 = fmaxf(x0, -125.f);
+    x1 = fmaxf(x1, -125.f);
+    float t0, t1, n0, n1, f0, f1, q0, q1;
+    add2(t0, t1, x0, x1, MAGIC, MAGIC);
+    add2(n0, n1, t0, t1, -MAGIC, -MAGIC);
+    fma2(f0, f1, n0, n1, -1.f, -1.f, x0, x1);
+    fma2(q0, q1, f0, f1, 0.055171459913f, 0.055171459913f, 0.24261085689f, 0.24261085689f);
+    fma2(q0, q1, q0, q1, f0, f1, 0.69326096773f, 0.69326096773f);
+    fma2(q0, q1, q0, q1, f0, f1, 0.9999281168f, 0.9999281168f);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 
+// POLY_MASK: bit (pair index mod 8) set -> that pair of scores takes the FMA-pipe exponential (0: all on the MUFU;
+// 0x88: one pair in four; 0x92: three in eight).
+// Exponential token between the two query groups, one per SM sub-partition (named barriers 1-4: group A's warp arrives,
+// group B's warp of the same sub-partition waits; 5-8 the other way round; 64 participants each): a warp starts the
+// exponentials of a tile only when the other group's warp on its sub-partition (the one it shares the MUFU with) has
+// passed score HANDOFF of its own tile.  This keeps the groups in ANTI-PHASE -- one group's TMEM round trips, row max
+// and barrier latencies run under the other group's MUFU-bound loop.  Left alone the groups lock IN phase (both in the
+// exponentials, then both outside them; profiles/r02_attention_trace.txt).
+__device__ __forceinline__ void named_bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+template <int POLY_MASK, int HANDOFF = 128>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                           // 2 buffers x 2 groups
-    uint8_t* sK = sQ + 4 * ATT_TILE_BYTES;        // 2 stages
-    uint8_t* sV = sK + 2 * ATT_TILE_BYTES;        // 2 stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * ATT_TILE_BYTES);
-    uint64_t* q_full = bars + 0;    // [2 buffers]   (bars + 0, bars + 23)
-    uint64_t* q_empty = bars + 21;  // [2 buffers]
-    uint64_t* k_full = bars + 1;    // [2 stages]
-    uint64_t* k_empty = bars + 3;
-    uint64_t* v_full = bars + 5;
-    uint64_t* v_empty = bars + 7;
-    uint64_t* s_full = bars + 9;    // [2 groups]  MMA -> softmax
-    uint64_t* s_free = bars + 11;   //             softmax -> MMA
-    uint64_t* p_full = bars + 13;   //             softmax -> MMA
-    uint64_t* o_full = bars + 17;   //             MMA -> softmax
-    uint64_t* o_free = bars + 19;   //             softmax -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+    uint8_t* sQ = smem;                                 // 2 buffers x 2 groups
+    uint8_t* sK = sQ + 4 * ATT_TILE_BYTES;              // ATT_KS stages
+    uint8_t* sV = sK + ATT_KS * ATT_TILE_BYTES;         // ATT_VS stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_VS * ATT_TILE_BYTES);
+    uint64_t* q_full = bars + 0;                        // [2 buffers]
+    uint64_t* q_empty = bars + 2;                       // [2 buffers]
+    uint64_t* k_full = bars + 4;                        // [ATT_KS]
+    uint64_t* k_empty = k_full + ATT_KS;
+    uint64_t* v_full = k_empty + ATT_KS;                // [ATT_VS]
+    uint64_t* v_empty = v_full + ATT_VS;
+    uint64_t* s_full = v_empty + ATT_VS;                // [2 groups]  MMA -> softmax : S_g(t) is in TMEM
+    uint64_t* s_free = s_full + 2;                      //             softmax -> MMA : S_g(t) has been pulled into registers
+    uint64_t* p_full = s_free + 2;                      //             softmax -> MMA : P_g(t) is in TMEM (and O_g rescaled if needed)
+    uint64_t* o_full = p_full + 2;                      //             MMA -> softmax : P_g(t) V(t) done (P consumed, O_g updated)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_kv = (args.N + ATT_BN - 1) / ATT_BN;
-    uint64_t* q_full1 = bars + 23;  // second Q buffer's full barrier
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.tmQKV);
-        mbar_init(q_full, 1);
-        mbar_init(q_full1, 1);
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
             mbar_init(&q_empty[i], 1);
-            mbar_init(&k_full[i], 1);
-            mbar_init(&k_empty[i], 1);
-            mbar_init(&v_full[i], 1);
-            mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&s_free[i], 4);
             mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1);
-            mbar_init(&o_free[i], 4);
+        }
+        for (int i = 0; i < ATT_KS; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+        }
+        for (int i = 0; i < ATT_VS; ++i) {
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
         }
         fence_mbar_init();
     }
@@ -124,88 +205,123 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && elect_one()) {
             // ===================================================== TMA producer
-            uint32_t it = 0;                                   // key-tile counter across work items
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
             int il = 0;                                        // local work-item counter
             for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++il) {
-                const int q0 = (w % args.n_qt) * ATT_BM;
-                const int head = (w / args.n_qt) % args.heads;
-                const int seq = w / (args.n_qt * args.heads);
+                const AttnItem item = attn_decode(args, w);
                 const int qb = il & 1;
-                uint64_t* qf = qb ? q_full1 : q_full;
                 mbar_wait(&q_empty[qb], ((il >> 1) & 1) ^ 1);
-                mbar_expect_tx(qf, 2 * ATT_TILE_BYTES);
-                tma_load_3d(sQ + (2 * qb) * ATT_TILE_BYTES, &args.tmQKV, qf, head * ATT_D, q0, seq);
-                tma_load_3d(sQ + (2 * qb + 1) * ATT_TILE_BYTES, &args.tmQKV, qf, head * ATT_D, q0 + 128, seq);
-                for (int j = 0; j < n_kv; ++j, ++it) {
-                    const int st = it & 1;
-                    const uint32_t ph = (it >> 1) & 1;
-                    mbar_wait(&k_empty[st], ph ^ 1);
-                    mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
-                    tma_load_3d(sK + st * ATT_TILE_BYTES, &args.tmQKV, &k_full[st], args.inner + head * ATT_D, j * ATT_BN, seq);
-                    mbar_wait(&v_empty[st], ph ^ 1);
-                    mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
-                    tma_load_3d(sV + st * ATT_TILE_BYTES, &args.tmQKV, &v_full[st], 2 * args.inner + head * ATT_D, j * ATT_BN,
-                                seq);
+                mbar_expect_tx(&q_full[qb], (item.two ? 2 : 1) * ATT_TILE_BYTES);
+                tma_load_3d(sQ + (2 * qb) * ATT_TILE_BYTES, &args.tmQKV, &q_full[qb], item.head * ATT_D, item.q0, item.seq);
+                if (item.two)
+                    tma_load_3d(sQ + (2 * qb + 1) * ATT_TILE_BYTES, &args.tmQKV, &q_full[qb], item.head * ATT_D, item.q0 + ATT_BG,
+                                item.seq);
+                for (int j = 0; j < n_kv; ++j) {
+                    mbar_wait(&k_empty[ks], kph ^ 1);
+                    mbar_expect_tx(&k_full[ks], ATT_TILE_BYTES);
+                    tma_load_3d(sK + ks * ATT_TILE_BYTES, &args.tmQKV, &k_full[ks], args.inner + item.head * ATT_D, j * ATT_BN,
+                                item.seq);
+                    if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
+                    mbar_wait(&v_empty[vs], vph ^ 1);
+                    mbar_expect_tx(&v_full[vs], ATT_TILE_BYTES);
+                    tma_load_3d(sV + vs * ATT_TILE_BYTES, &args.tmQKV, &v_full[vs], 2 * args.inner + item.head * ATT_D,
+                                j * ATT_BN, item.seq);
+                    if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
                 }
             }
         } else if (warp == 1 && elect_one()) {
             // ===================================================== MMA issuer (elect.sync: ptxas keeps operands in uniform registers)
             constexpr uint32_t idesc_s = make_idesc_f16(128, ATT_BN, 1, 0, 0);   // Q K^T : both K-major
             constexpr uint32_t idesc_o = make_idesc_f16(128, ATT_D, 1, 0, 1);    // P V   : V is MN-major
-            // Descriptors are built once; per MMA only the 14-bit start-address field is advanced (one add), so the
-            // single issuing thread never becomes the bottleneck (24 MMAs per key tile).
-            uint64_t dQ[4], dK[2], dV[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                dK[i] = smem_desc_sw128(smem_u32(sK + i * ATT_TILE_BYTES), 1024, 16);
-                dV[i] = smem_desc_sw128(smem_u32(sV + i * ATT_TILE_BYTES), 1024, ATT_TILE_BYTES);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dQ[i] = smem_desc_sw128(smem_u32(sQ + i * ATT_TILE_BYTES), 1024, 16);
-            // One software pipeline over ALL key tiles of ALL work items of this CTA: at step t issue S(t), then P(t-1) V(t-1).
+            // Descriptors of buffer 0; per MMA only the 14-bit start-address field is advanced.
+            const uint64_t dQ0 = smem_desc_sw128(smem_u32(sQ), 1024, 16);
+            const uint64_t dK0 = smem_desc_sw128(smem_u32(sK), 1024, 16);
+            const uint64_t dV0 = smem_desc_sw128(smem_u32(sV), 1024, ATT_TILE_BYTES);
             int n_my = 0;
             for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) ++n_my;
             const uint32_t total = static_cast<uint32_t>(n_my) * n_kv;
-            int il = 0, j = 0;                                 // work item / key tile of step t
-            for (uint32_t t = 0; t <= total; ++t) {
-                if (t < total) {
-                    const int qb = il & 1;
-                    if (j == 0) mbar_wait(qb ? q_full1 : q_full, (il >> 1) & 1);
-                    const int st = t & 1;
-                    mbar_wait(&k_full[st], (t >> 1) & 1);
-                    const uint64_t bK = st ? dK[1] : dK[0];
+            // cursor of step u (the S tile) and the descriptors of the two previous steps (their PV products)
+            int il = 0, j = 0, w = blockIdx.x;
+            int two_c = n_my > 0 ? attn_decode(args, w).two : 0;
+            int ks = 0;
+            uint32_t kph = 0;
+            int j1 = 0, two1 = 0, j2 = 0, two2 = 0;           // (j, two) of steps u-1 and u-2
+            uint32_t cS0 = 0, cS1 = 0, cP0 = 0, cP1 = 0;      // S / PV products issued per group (barrier parities)
+            for (uint32_t u = 0; u <= total + 1; ++u) {
+                const bool have = u < total;
+                const int qb = il & 1;
+                // ---- S_A(u)
+                if (have) {
+                    if (j == 0) mbar_wait(&q_full[qb], (il >> 1) & 1);
+                    mbar_wait(&k_full[ks], kph);
+                    mbar_wait(&s_free[0], (cS0 & 1) ^ 1);          // softmax A has pulled S_A(u-1) into registers
+                    tc_fence_after();
+                    const uint64_t bQ = desc_advance(dQ0, (2 * qb) * ATT_TILE_BYTES);
+                    const uint64_t bK = desc_advance(dK0, ks * ATT_TILE_BYTES);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        mbar_wait(&s_free[g], (t & 1) ^ 1);        // softmax has pulled S_g(t-1) into registers
+                    for (int k = 0; k < ATT_D / 16; ++k)
+                        umma_f16(tmem_S, desc_advance(bQ, k * 32), desc_advance(bK, k * 32), idesc_s, k != 0);
+                    umma_commit(&s_full[0]);
+                    ++cS0;
+                }
+                // ---- O_B += P_B(u-2) V(u-2)
+                if (u >= 2 && u - 2 < total && two2) {
+                    const uint32_t tt = u - 2;
+                    const int vs = tt % ATT_VS;
+                    mbar_wait(&v_full[vs], (tt / ATT_VS) & 1);
+                    mbar_wait(&p_full[1], cP1 & 1);
+                    tc_fence_after();
+                    const uint64_t bV = desc_advance(dV0, vs * ATT_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < ATT_BN / 16; ++k)
+                        umma_f16_ts(tmem_O + ATT_D, tmem_P + 64 + k * 8, desc_advance(bV, k * 2048), idesc_o, (k != 0) || (j2 != 0));
+                    umma_commit(&o_full[1]);
+                    umma_commit(&v_empty[vs]);
+                    ++cP1;
+                }
+                // ---- S_B(u), then K(u) (and after the item's last tile its Q buffer) can be refilled
+                if (have) {
+                    if (two_c) {
+                        mbar_wait(&s_free[1], (cS1 & 1) ^ 1);
                         tc_fence_after();
-                        const uint64_t bQ = qb ? dQ[2 + g] : dQ[g];
+                        const uint64_t bQ = desc_advance(dQ0, (2 * qb + 1) * ATT_TILE_BYTES);
+                        const uint64_t bK = desc_advance(dK0, ks * ATT_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < ATT_D / 16; ++k)
-                            umma_f16(tmem_S + g * ATT_BN, desc_advance(bQ, k * 32), desc_advance(bK, k * 32), idesc_s, k != 0);
-                        umma_commit(&s_full[g]);
+                            umma_f16(tmem_S + ATT_BN, desc_advance(bQ, k * 32), desc_advance(bK, k * 32), idesc_s, k != 0);
+                        umma_commit(&s_full[1]);
+                        ++cS1;
                     }
-                    umma_commit(&k_empty[st]);
-                    if (j == n_kv - 1) umma_commit(&q_empty[qb]);  // last S of this item: its Q buffer may be refilled
-                    if (++j == n_kv) { j = 0; ++il; }
+                    umma_commit(&k_empty[ks]);
+                    if (j == n_kv - 1) umma_commit(&q_empty[qb]);
+                    if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
                 }
-                if (t >= 1) {
-                    const uint32_t tt = t - 1;
-                    const int st = tt & 1;
-                    mbar_wait(&v_full[st], (tt >> 1) & 1);
-                    const uint64_t bV = st ? dV[1] : dV[0];
+                // ---- O_A += P_A(u-1) V(u-1)
+                if (u >= 1 && u - 1 < total) {
+                    const uint32_t tt = u - 1;
+                    const int vs = tt % ATT_VS;
+                    mbar_wait(&v_full[vs], (tt / ATT_VS) & 1);
+                    mbar_wait(&p_full[0], cP0 & 1);
+                    tc_fence_after();
+                    const uint64_t bV = desc_advance(dV0, vs * ATT_TILE_BYTES);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        mbar_wait(&p_full[g], tt & 1);
-                        mbar_wait(&o_free[g], (tt & 1) ^ 1);
-                        tc_fence_after();
-#pragma unroll
-                        for (int k = 0; k < ATT_BN / 16; ++k) {
-                            // A = P from TMEM (16 keys = 8 columns per step); B = V: MN-major, 16 keys = 2048 B apart
-                            umma_f16_ts(tmem_O + g * ATT_D, tmem_P + g * 64 + k * 8, desc_advance(bV, k * 2048), idesc_o, k != 0);
-                        }
-                        umma_commit(&o_full[g]);                   // also means: P_g has been consumed
-                    }
-                    umma_commit(&v_empty[st]);
+                    for (int k = 0; k < ATT_BN / 16; ++k)
+                        umma_f16_ts(tmem_O, tmem_P + k * 8, desc_advance(bV, k * 2048), idesc_o, (k != 0) || (j1 != 0));
+                    umma_commit(&o_full[0]);
+                    if (!two1) umma_commit(&v_empty[vs]);          // single-group item: nobody else reads V(u-1)
+                    ++cP0;
+                }
+                // ---- advance: step u becomes u-1, u-1 becomes u-2
+                j2 = j1;
+                two2 = two1;
+                j1 = j;
+                two1 = two_c;
+                if (have && ++j == n_kv) {
+                    j = 0;
+                    ++il;
+                    w += gridDim.x;
+                    if (w < args.n_items) two_c = attn_decode(args, w).two;
                 }
             }
         }
@@ -213,141 +329,195 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================================================== softmax warpgroups: thread == query row
         const int g = (warp - 4) >> 2;                 // 0: group A (warps 4-7), 1: group B (warps 8-11)
-        const int lq = warp & 3;                       // TMEM lane quarter
+        const int lq = warp & 3;                       // TMEM lane quarter == SM sub-partition of this warp
         const int row = lq * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lq * 32) << 16;
         const uint32_t tS = tmem_S + g * ATT_BN + lane_addr;
         const uint32_t tO = tmem_O + g * ATT_D + lane_addr;
-        const float c = args.scale_log2e;
-        float acc[ATT_D];
-        uint32_t it = 0;             // key-tile counter across work items (barrier parities)
         const uint32_t tP = tmem_P + g * 64 + lane_addr;
-
-        auto accumulate_O = [&](uint32_t t, float alpha) {
-            mbar_wait(&o_full[g], t & 1);
-            tc_fence_after();
-            uint32_t o[64];
-            uint32_t (&o0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
-            uint32_t (&o1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[32]);
-            tmem_ld_32x32(tO, o0);
-            tmem_ld_32x32(tO + 32, o1);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[g]);
-#pragma unroll
-            for (int d = 0; d < ATT_D; ++d) acc[d] = fmaf(acc[d], alpha, __uint_as_float(o[d]));
-        };
+        constexpr float c = 0.125f * 1.4426950408889634f;   // dim_head^-0.5 * log2(e); dim_head is 64 in this library
+        uint32_t itg = 0;            // key tiles this group has processed (barrier parities)
+        uint32_t itp = 0;            // ... of which in pair items (token hand-offs with the other group)
+        bool s_ready = false;        // s_full of the coming tile has already been observed complete
 
         for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
-        const int q0 = (w % args.n_qt) * ATT_BM;
-        const int head = (w / args.n_qt) % args.heads;
-        const int seq = w / (args.n_qt * args.heads);
-        float m_run = -INFINITY;     // running max of raw scores
-        float l_run = 0.f;           // running sum of exp
-        float alpha_prev = 0.f;      // rescale factor belonging to the O tile not yet accumulated
+            const AttnItem item = attn_decode(args, w);
+            if (g == 1 && !item.two) continue;
+            const bool ho = HANDOFF > 0 && args.stagger != 0 && item.two;
+            float m_run = -INFINITY;     // reference maximum of the raw scores (lags the true running max by < 2^8 / c)
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;     // running sum of p (four partial sums)
+            for (int j = 0; j < n_kv; ++j, ++itg) {
+                TR(0);
+                if (!s_ready) mbar_wait(&s_full[g], itg & 1);
+                TR(1);
+                tc_fence_after();
+                uint32_t s[128];
+                {
+                    uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+                    uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+                    uint32_t (&s2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[64]);
+                    uint32_t (&s3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[96]);
+                    tmem_ld_32x32(tS, s0);
+                    tmem_ld_32x32(tS + 32, s1);
+                    tmem_ld_32x32(tS + 64, s2);
+                    tmem_ld_32x32(tS + 96, s3);
+                    tmem_ld_wait();
+                }
+                // S is in registers: the MMA warp may overwrite the buffer with S(j+1)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[g]);
+                TR(2);
+
+                const int kv_valid = args.N - j * ATT_BN;      // keys >= kv_valid are padding (last tile only)
+                if (kv_valid < ATT_BN) {
 #pragma unroll
-        for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
-        for (int j = 0; j < n_kv; ++j, ++it) {
-            TR(0);
-            mbar_wait(&s_full[g], it & 1);
-            TR(1);
+                    for (int i = 0; i < 128; ++i)
+                        if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+                }
+                // row max: 8 independent chains of three-input max (dependency depth 8 instead of 32)
+                float mx[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(s[i]);
+#pragma unroll
+                for (int i = 8; i + 15 < 128; i += 16) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) mx[q] = fmax3(mx[q], __uint_as_float(s[i + 2 * q]), __uint_as_float(s[i + 2 * q + 1]));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) mx[q] = fmax3(mx[q], __uint_as_float(s[120 + 2 * q]), __uint_as_float(s[121 + 2 * q]));
+                const float m_tile = fmaxf(fmaxf(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5])), fmaxf(mx[6], mx[7]));
+                TR(3);
+                // Raise the reference maximum only when some row of this warp would otherwise exceed 2^8 (warp-uniform
+                // decision: the TMEM accesses of the rescale are warp-collective).  alpha = 1 for the rows that did not move.
+                float alpha = 1.0f;
+                bool rescale = false;
+                if (j == 0) {
+                    m_run = m_tile;                                 // O and l start from zero: nothing to rescale
+                } else {
+                    const float m_new = fmaxf(m_run, m_tile);
+                    if (__any_sync(0xffffffffu, (m_new - m_run) * c > ATT_RESCALE_LOG2)) {
+                        alpha = ex2_approx((m_run - m_new) * c);
+                        m_run = m_new;
+                        rescale = true;
+                        mul2(l0, l1, l0, l1, alpha, alpha);
+                        mul2(l2, l3, l2, l3, alpha, alpha);
+                    }
+                }
+                const float mc = -m_run * c;
+                // The P buffer is free (and O_g up to date) once the PV product of this group's previous tile has completed:
+                // poll that barrier now, consume the answer half-way through the exponentials (even a completed mbarrier costs ~100 cycles)
+                const bool o_ready = itg > 0 ? mbar_try_wait(&o_full[g], (itg - 1) & 1) : true;
+                // token: A's pair tile p starts after B's hand-off point of tile p-1, B's tile p after A's of tile p
+                if (ho && (g == 1 || itp > 0)) named_bar_sync64(g == 0 ? 5 + lq : 1 + lq);
+                // p = exp2(s*c - m*c) -> bf16 pairs packed in place (s[0..63] = P); the row sum is taken in fp32 before rounding
+                const bool all_mufu = (POLY_MASK == 0) || (kv_valid < ATT_BN);    // -inf scores only go through the MUFU
+                if (all_mufu) {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 4) {
+                        if (i == HANDOFF && ho) named_bar_arrive64(g == 0 ? 1 + lq : 5 + lq);
+                        if (i == 64) {                       // first half of P goes to TMEM under the second half's exponentials
+                            if (!o_ready) mbar_wait(&o_full[g], (itg - 1) & 1);
+                            tc_fence_after();
+                            if (!rescale) tmem_st_32x32(tP, &s[0]);
+                        }
+                        if (i == 96) s_ready = (j + 1 < n_kv) ? mbar_try_wait(&s_full[g], (itg + 1) & 1) : false;
+                        float x0, x1, x2, x3;
+                        fma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, c, mc, mc);
+                        fma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), c, c, mc, mc);
+                        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+                        add2(l0, l1, l0, l1, p0, p1);
+                        add2(l2, l3, l2, l3, p2, p3);
+                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1);
+                        const __nv_bfloat162 h23 = __floats2bfloat162_rn(p2, p3);
+                        s[i >> 1] = *reinterpret_cast<const uint32_t*>(&h01);
+                        s[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 4) {
+                        if (i == HANDOFF && ho) named_bar_arrive64(g == 0 ? 1 + lq : 5 + lq);
+                        if (i == 64) {                       // first half of P goes to TMEM under the second half's exponentials
+                            if (!o_ready) mbar_wait(&o_full[g], (itg - 1) & 1);
+                            tc_fence_after();
+                            if (!rescale) tmem_st_32x32(tP, &s[0]);
+                        }
+                        if (i == 96) s_ready = (j + 1 < n_kv) ? mbar_try_wait(&s_full[g], (itg + 1) & 1) : false;
+                        float x0, x1, x2, x3, p0, p1, p2, p3;
+                        fma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, c, mc, mc);
+                        fma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), c, c, mc, mc);
+                        if ((POLY_MASK >> ((i >> 1) & 7)) & 1) exp2_fma2(p0, p1, x0, x1);
+                        else { p0 = ex2_approx(x0); p1 = ex2_approx(x1); }
+                        if ((POLY_MASK >> (((i >> 1) + 1) & 7)) & 1) exp2_fma2(p2, p3, x2, x3);
+                        else { p2 = ex2_approx(x2); p3 = ex2_approx(x3); }
+                        add2(l0, l1, l0, l1, p0, p1);
+                        add2(l2, l3, l2, l3, p2, p3);
+                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1);
+                        const __nv_bfloat162 h23 = __floats2bfloat162_rn(p2, p3);
+                        s[i >> 1] = *reinterpret_cast<const uint32_t*>(&h01);
+                        s[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                    }
+                }
+                if (HANDOFF >= 128 && ho) named_bar_arrive64(g == 0 ? 1 + lq : 5 + lq);
+                itp += item.two;
+                TR(4);
+                TR(5);
+                if (rescale) {
+                    uint32_t o[64];
+                    uint32_t (&o0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
+                    uint32_t (&o1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[32]);
+                    tmem_ld_32x32(tO, o0);
+                    tmem_ld_32x32(tO + 32, o1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int d = 0; d < ATT_D; d += 2) {
+                        float a0, a1;
+                        mul2(a0, a1, __uint_as_float(o[d]), __uint_as_float(o[d + 1]), alpha, alpha);
+                        o[d] = __float_as_uint(a0);
+                        o[d + 1] = __float_as_uint(a1);
+                    }
+                    tmem_st_32x32(tO, &o[0]);
+                    tmem_st_32x32(tO + 32, &o[32]);
+                    tmem_st_32x32(tP, &s[0]);
+                }
+                // P -> TMEM: thread = row, column i = keys (2i, 2i+1) as a bf16 pair (the first half is already on its way)
+                tmem_st_32x32(tP + 32, &s[32]);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[g]);
+                TR(6);
+            }
+            // ---- item epilogue: O_g / l from TMEM (the next item's first PV product, which overwrites O_g, is only issued
+            // after this thread's next p_full arrival)
+            mbar_wait(&o_full[g], (itg - 1) & 1);
             tc_fence_after();
-            uint32_t s[128];
+            uint32_t o[64];
             {
-                uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
-                uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
-                uint32_t (&s2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[64]);
-                uint32_t (&s3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[96]);
-                tmem_ld_32x32(tS, s0);
-                tmem_ld_32x32(tS + 32, s1);
-                tmem_ld_32x32(tS + 64, s2);
-                tmem_ld_32x32(tS + 96, s3);
+                uint32_t (&o0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
+                uint32_t (&o1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[32]);
+                tmem_ld_32x32(tO, o0);
+                tmem_ld_32x32(tO + 32, o1);
                 tmem_ld_wait();
             }
-            // S is in registers: the MMA warp may overwrite the buffer with S(j+1)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[g]);
-            TR(2);
-
-            const int kv_valid = args.N - j * ATT_BN;      // keys >= kv_valid are padding (last tile only)
-            if (kv_valid < ATT_BN) {
+            const int qpos = item.q0 + g * ATT_BG + row;
+            if (qpos < args.N) {
+                const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
+                __nv_bfloat16* dst = args.out + (static_cast<size_t>(item.seq) * args.N + qpos) * args.inner + item.head * ATT_D;
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
-                    if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+                for (int d = 0; d < ATT_D; d += 8) {
+                    uint4 v;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(o[d]) * inv, __uint_as_float(o[d + 1]) * inv);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(o[d + 2]) * inv, __uint_as_float(o[d + 3]) * inv);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(o[d + 4]) * inv, __uint_as_float(o[d + 5]) * inv);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(o[d + 6]) * inv, __uint_as_float(o[d + 7]) * inv);
+                    v.x = *reinterpret_cast<uint32_t*>(&h0);
+                    v.y = *reinterpret_cast<uint32_t*>(&h1);
+                    v.z = *reinterpret_cast<uint32_t*>(&h2);
+                    v.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(dst + d) = v;
+                }
             }
-            // row max: 8 independent chains of three-input max (dependency depth 8 instead of 32)
-            float mx[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(s[i]);
-#pragma unroll
-            for (int i = 8; i + 15 < 128; i += 16) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) mx[q] = fmax3(mx[q], __uint_as_float(s[i + 2 * q]), __uint_as_float(s[i + 2 * q + 1]));
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) mx[q] = fmax3(mx[q], __uint_as_float(s[120 + 2 * q]), __uint_as_float(s[121 + 2 * q]));
-            const float mx0 = fmax3(mx[0], mx[1], mx[2]), mx1 = fmax3(mx[3], mx[4], mx[5]), mx2 = fmaxf(mx[6], mx[7]), mx3 = mx2;
-            const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-            TR(3);
-            const float alpha = ex2_approx((m_run - m_new) * c);    // first tile: exp2(-inf) = 0
-            const float mc = m_new * c;
-            // p = exp2(s*c - m*c) -> bf16 pairs; the row sum is taken in fp32 before rounding
-            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 128; i += 4) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, -mc));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, -mc));
-                const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), c, -mc));
-                const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), c, -mc));
-                const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1);
-                const __nv_bfloat162 h23 = __floats2bfloat162_rn(p2, p3);
-                l0 += p0;
-                l1 += p1;
-                l2 += p2;
-                l3 += p3;
-                s[i >> 1] = *reinterpret_cast<const uint32_t*>(&h01);          // pack in place: s[0..63] = P
-                s[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-            }
-            TR(4);
-            // P must have been consumed by the PV MMA of the previous tile: that is the same commit that publishes
-            // O(it-1), so wait for it once here and fold the previous tile's O into the accumulator right away
-            if (j > 0) accumulate_O(it - 1, alpha_prev);
-            TR(5);
-            // P -> TMEM: thread = row, column i = keys (2i, 2i+1) as a bf16 pair
-            tmem_st_32x32(tP, &s[0]);
-            tmem_st_32x32(tP + 32, &s[32]);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[g]);
-            TR(6);
-            l_run = fmaf(l_run, alpha, (l0 + l1) + (l2 + l3));
-            m_run = m_new;
-            TR(7);
-            alpha_prev = alpha;
-        }
-        accumulate_O(it - 1, alpha_prev);
-
-        const int qpos = q0 + g * 128 + row;
-        if (qpos < args.N) {
-            const float inv = 1.0f / l_run;
-            __nv_bfloat16* dst = args.out + (static_cast<size_t>(seq) * args.N + qpos) * args.inner + head * ATT_D;
-#pragma unroll
-            for (int d = 0; d < ATT_D; d += 8) {
-                uint4 v;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[d] * inv, acc[d + 1] * inv);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[d + 2] * inv, acc[d + 3] * inv);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[d + 4] * inv, acc[d + 5] * inv);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[d + 6] * inv, acc[d + 7] * inv);
-                v.x = *reinterpret_cast<uint32_t*>(&h0);
-                v.y = *reinterpret_cast<uint32_t*>(&h1);
-                v.z = *reinterpret_cast<uint32_t*>(&h2);
-                v.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(dst + d) = v;
-            }
-        }
         }   // work items
     }
 

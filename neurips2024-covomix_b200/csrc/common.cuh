@@ -337,6 +337,58 @@ inline int launch_gemm(const GemmOp& op, cudaStream_t st) {
     return COVO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ attention launch
+// Tunables of attention_tc_kernel (defaults chosen from tools/micro/attn_bench.cu on B200, profiles/r02_attention_bench.txt;
+// overridable for A/B runs):
+//   COVO_ATT_POLY    0: every exponential on the MUFU, 1 (default): one pair in four on the FMA pipe, 2: three pairs in eight
+//   COVO_ATT_TOKEN   1: exponential token between the two query groups (anti-phase); default 0 (free running) -- the token
+//                    costs as much as it hides while one warp per sub-partition cannot saturate the MUFU on its own
+struct AttnTune {
+    int poly = 1;
+    int stagger = 0;
+};
+inline AttnTune& attn_tune() {
+    static AttnTune t;
+    static bool init = false;
+    if (!init) {
+        if (const char* v = getenv("COVO_ATT_POLY")) t.poly = atoi(v);
+        if (const char* v = getenv("COVO_ATT_TOKEN")) t.stagger = atoi(v);
+        init = true;
+    }
+    return t;
+}
+inline int attn_set_attrs() {
+    COVO_CK(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    COVO_CK(cudaFuncSetAttribute(attention_tc_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    COVO_CK(cudaFuncSetAttribute(attention_tc_kernel<0x92>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    return COVO_OK;
+}
+// qkv: bf16 [Bt, N, 3*heads*64] (the to_qkv output, RoPE applied); out: bf16 [Bt, N, heads*64]
+inline int attn_build_args(AttnArgs& a, const void* qkv, void* out, int Bt, int N, int heads) {
+    const int inner = heads * ATT_D;
+    uint64_t dims[3] = {static_cast<uint64_t>(3 * inner), static_cast<uint64_t>(N), static_cast<uint64_t>(Bt)};
+    uint64_t str[2] = {static_cast<uint64_t>(3 * inner) * 2, static_cast<uint64_t>(3 * inner) * 2 * N};
+    uint32_t box[3] = {64, 128, 1};
+    COVO_TRY(make_tmap(&a.tmQKV, qkv, 3, dims, str, box, 0));
+    a.out = static_cast<__nv_bfloat16*>(out);
+    a.N = N;
+    a.heads = heads;
+    a.inner = inner;
+    a.stagger = attn_tune().stagger;
+    attn_fill_items(a, Bt);
+    return COVO_OK;
+}
+inline int launch_attention_kernel(const AttnArgs& a, int num_sms, cudaStream_t st) {
+    const int grid = a.n_items < num_sms ? a.n_items : num_sms;
+    switch (attn_tune().poly) {
+        case 0: attention_tc_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a); break;
+        case 2: attention_tc_kernel<0x92><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a); break;
+        default: attention_tc_kernel<0x88><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a); break;
+    }
+    COVO_CK(cudaGetLastError());
+    return COVO_OK;
+}
+
 // bump allocator over the caller's workspace
 struct Arena {
     uint8_t* base;

@@ -27,7 +27,7 @@ int init_kernel_attrs() {
     COVO_TRY((set_gemm_attr<256, 0>()));
     COVO_TRY((set_gemm_attr<128, 0>()));
     COVO_TRY((set_gemm_attr<64, 0>()));
-    COVO_CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    COVO_TRY(attn_set_attrs());
     COVO_CK(cudaFuncSetAttribute(hifigan_fused_last_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(HF_SMEM_BYTES)));
     COVO_CK(cudaFuncSetAttribute(hifigan_fused_last_stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -597,19 +597,8 @@ int covo_dbg_attention(const void* qkv_bf16, void* out_bf16, int Bt, int N, int 
                                                      static_cast<__nv_bfloat16*>(out_bf16), N, heads, inner, 0.125f);
     } else {
         AttnArgs a;
-        uint64_t dims[3] = {static_cast<uint64_t>(3 * inner), static_cast<uint64_t>(N), static_cast<uint64_t>(Bt)};
-        uint64_t str[2] = {static_cast<uint64_t>(3 * inner) * 2, static_cast<uint64_t>(3 * inner) * 2 * N};
-        uint32_t box[3] = {64, 128, 1};
-        COVO_TRY(make_tmap(&a.tmQKV, qkv_bf16, 3, dims, str, box, 0));
-        a.out = static_cast<__nv_bfloat16*>(out_bf16);
-        a.N = N;
-        a.heads = heads;
-        a.inner = inner;
-        a.scale_log2e = 1.4426950408889634f * 0.125f;
-        a.n_qt = ceil_div(N, ATT_BM);
-        a.n_items = a.n_qt * heads * Bt;
-        const int grid = a.n_items < di.num_sms ? a.n_items : di.num_sms;
-        attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+        COVO_TRY(attn_build_args(a, qkv_bf16, out_bf16, Bt, N, heads));
+        COVO_TRY(launch_attention_kernel(a, di.num_sms, st));
     }
     COVO_CK(cudaGetLastError());
     return COVO_OK;

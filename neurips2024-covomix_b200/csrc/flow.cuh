@@ -260,19 +260,8 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
     p.op_pred.flops = 2.0 * M * D * c.dim_x;
 
     // attention
-    {
-        uint64_t dims[3] = {static_cast<uint64_t>(3 * inner), static_cast<uint64_t>(p.N), static_cast<uint64_t>(M / p.N)};
-        uint64_t str[2] = {static_cast<uint64_t>(3 * inner) * 2, static_cast<uint64_t>(3 * inner) * 2 * p.N};
-        uint32_t box[3] = {64, 128, 1};
-        COVO_TRY(make_tmap(&p.attn.tmQKV, p.qkv, 3, dims, str, box, 0));
-        p.attn.out = p.attn_o;
-        p.attn.N = p.N;
-        p.attn.heads = c.heads;
-        p.attn.inner = inner;
-        p.attn.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(c.dim_head));
-        p.attn.n_qt = ceil_div(p.N, ATT_BM);
-        p.attn.n_items = p.attn.n_qt * c.heads * (M / p.N);
-    }
+    if (c.dim_head != ATT_D) return fail(COVO_ERR_INVALID, "dim_head=%d unsupported (64 only)", c.dim_head);
+    COVO_TRY(attn_build_args(p.attn, p.qkv, p.attn_o, M / p.N, p.N, c.heads));
     return COVO_OK;
 }
 
@@ -284,13 +273,7 @@ inline int launch_attention(const covo_flow* h, const FlowPlan& p, cudaStream_t 
         naive_attention_kernel<<<grid, 256, 0, st>>>(p.qkv, p.attn_o, p.N, h->cfg.heads, p.attn.inner,
                                                      1.0f / sqrtf(static_cast<float>(h->cfg.dim_head)));
     } else {
-        static bool attr = false;
-        if (!attr) {
-            COVO_CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-            attr = true;
-        }
-        const int grid = p.attn.n_items < h->di.num_sms ? p.attn.n_items : h->di.num_sms;
-        attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(p.attn);
+        COVO_TRY(launch_attention_kernel(p.attn, h->di.num_sms, st));
     }
     COVO_CK(cudaGetLastError());
     return COVO_OK;

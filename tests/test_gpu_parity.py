@@ -227,8 +227,9 @@ def test_reused_workspace_with_garbage_padding(dev, vosingle, vocoder):
     mel = syn.synthetic_logmel(torch.Generator().manual_seed(3), 2, 80, 40).to(dev)
     wa = gen(mel)
     torch.cuda.synchronize()
-    for ws in list(smp._ws.values()) + list(gen._ws.values()):
-        ws.fill_(0xFF)
+    with torch.inference_mode():                    # the cached workspaces were allocated under inference_mode
+        for ws in list(smp._ws.values()) + list(gen._ws.values()):
+            ws.fill_(0xFF)
     b = smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
     vb = smp.velocity(y0.to(dev), times=0.5, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
     wb = gen(mel)
