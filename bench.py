@@ -128,6 +128,19 @@ def ncu_traffic_per_launch():
     return sum(vals) / len(vals) if vals else None
 
 
+def config_for(wl, world, t2s_sms=0, flow_sms=None):
+    """The `config` object of the JSON line: identical for the B200 arm and the reference arm (the driver compares them)."""
+    cfg = {"workload": wl["name"], "global_batch": wl["B"] * world, "seq_len": wl["N"],
+           "parallelism": f"utterance-sharded x{world}", "cond_scale": 0.7,
+           "sm_budget": {"t2s": t2s_sms, "flow+vocoder": "all other SMs"} if t2s_sms else None,
+           "l2": "working set (0.8 GB weights + 1.2 GB activations) larger than L2; no flush needed"}
+    if "t2s" in wl:
+        cfg["t2s_assumption"] = ("text-to-semantic decodes the 8 dialogues of a batch in ONE call with EOS ignored (random-init weights "
+                                 "would stop at a random position); covomix_b200.pipeline.covomix_dialogues decodes one dialogue per "
+                                 "call like the reference, because its EOS rule couples the rows of a batch")
+    return cfg
+
+
 def make_inputs(wl, device=None, seed=30):
     from covomix_b200 import synthetic as syn
     cfg = syn.VOMIX if wl["model"] == "vomix" else syn.VOSINGLE
@@ -204,21 +217,22 @@ def run_reference(args):
         "impl": "reference", "metric": "audio-seconds/sec (RTF)", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "global_batch": wl["B"], "seq_len": wl["N"]},
+        "config": config_for(wl, max(1, args.gpus), int(os.environ.get("COVO_T2S_SMS", wl.get("t2s_sms", 0))),
+                             None),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ode_step_ms": tv * 1e3 * wl["B"],
     }
+    if args.workload == "c3":
+        line["cpu_baseline"]["c2_measured"] = cpu_c2_measured()
     print(json.dumps(line), flush=True)
 
 
 # ======================================================================================== B200 arm
 def run_b200(args):
-    import covomix_b200  # noqa: F401
-    from covomix_b200 import _native as nat, synthetic as syn
-    from covomix_b200.flow import B200FlowSampler
-    from covomix_b200.vocoder import B200Generator
-
+    """Default run: the headline workload (one JSON line, the bench contract) -- and, for the default workload c3, the other
+    BASELINE configs measured in the same process right after it and attached under `other_configs` (C2, C4 pipelined,
+    the C5 vocoder sweep), so that every BASELINE config is on the driver's record at every N."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,9 +245,44 @@ def run_b200(args):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
+    ctx = dict(world=world, rank=rank, local=local, dev=dev, dist=dist)
+    line = bench_workload(args, args.workload, ctx, detail=True)
+    if args.workload == "c3" and not args.no_other_configs:
+        others = {}
+        for key, steps in (("c2", 5), ("c4p", 2)):
+            try:
+                sub = bench_workload(argparse.Namespace(**{**vars(args), "steps": steps, "no_cpu_baseline": True}), key, ctx,
+                                     detail=False)
+                if sub is not None:
+                    others[key] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "n_gpus", "steps", "warmup", "config", "e2e",
+                                                       "ode_step_ms", "clocks", "gpu_launches") if k in sub}
+            except Exception as e:                      # the headline line must survive a failure of an attached config
+                others[key] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            sweep = run_vocoder_sweep(args, ctx, quiet=True)
+            if sweep is not None:
+                others["c5"] = sweep
+        except Exception as e:
+            others["c5"] = {"error": f"{type(e).__name__}: {e}"}
+        if line is not None:
+            line["other_configs"] = others
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
 
-    wl = WORKLOADS[args.workload]
-    cfg, ids_h, cond_h, y0_h, mask_h = make_inputs(wl, seed=30 + rank)     # each rank = its own shard of utterances
+
+def bench_workload(args, wl_key, ctx, detail=True):
+    import covomix_b200  # noqa: F401
+    from covomix_b200 import _native as nat, synthetic as syn
+    from covomix_b200.flow import B200FlowSampler
+    from covomix_b200.vocoder import B200Generator
+
+    world, rank, local, dev, dist = ctx["world"], ctx["rank"], ctx["local"], ctx["dev"], ctx["dist"]
+    wl = WORKLOADS[wl_key]
+    cfg, ids_h, cond_h, y0_h, mask_h = make_inputs(wl, seed=30 + rank)    # each rank = its own shard of utterances
     # weights: identical on every rank (seeded); rank 0 could equally broadcast them (NCCL) -- see DESIGN.md
     n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
     t2s_sms = int(os.environ.get("COVO_T2S_SMS", wl.get("t2s_sms", 0)))
@@ -362,7 +411,19 @@ def run_b200(args):
         e1.record()
         torch.cuda.synchronize()
         ode_step_ms = e0.elapsed_time(e1) / 3
+        launches = (sampler.launches_per_sample(0.7) + gen.launches_per_forward()) * K + (t2s.launches_per_generate() * K if t2s is not None else 0)
+        line = {
+            "metric": "audio-seconds/sec (RTF)", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 operands / f32 accumulate (flow), fp16 operands / f32 accumulate (vocoder)", "data": "synthetic",
+            "config": config_for(wl, world, t2s_sms, flow_sms),
+            "clocks": clocks, "gpu_launches": launches * world,
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "ode_step_ms": ode_step_ms,
+        }
 
+    if rank == 0 and detail:
         # ---- roofline of the dominant kernel: one extra instrumented step (graphs bypassed, every launch of the
         # step bracketed by CUDA events on the launching stream), same workload, same process
         with nat.profile() as prof:
@@ -379,7 +440,7 @@ def run_b200(args):
             "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM), launches of the velocity net's Linear layers",
             "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["tflops"], "peak_source": pk["src"],
-            "traffic": ncu_traffic_per_launch() if args.workload == "c3" else None,
+            "traffic": ncu_traffic_per_launch() if wl_key == "c3" else None,
             "traffic_note": "mean dram__bytes_read+write per GEMM launch over the 8 launches of profiles/r01_gemm_c3_ncu.md (bytes)",
             "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "algorithmic_flops_per_launch": g_flops / max(g_n, 1),
             "share_of_step_kernel_time": g_ms / total_kernel_ms if total_kernel_ms else None,
@@ -392,10 +453,8 @@ def run_b200(args):
                            "achieved_tflops": (flow_fl + voc_fl) / (ms_step * 1e-3) / 1e12,
                            "frac_of_peak": (flow_fl + voc_fl) / (ms_step * 1e-3) / 1e12 / pk["tflops"]},
         }
-        launches = (sampler.launches_per_sample(0.7) + gen.launches_per_forward()) * K
         t2s_info = None
         if t2s is not None:
-            launches += t2s.launches_per_generate() * K
             d_ms = pr["t2s_decode"][0]
             steps_t = wl["t2s"]["steps"]
             gbs = t2s.weight_bytes_per_step() * steps_t / (d_ms * 1e-3) / 1e9 if d_ms else None
@@ -410,48 +469,78 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(wl, cfg)
 
-        line = {
-            "metric": "audio-seconds/sec (RTF)", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 operands / f32 accumulate (flow), fp16 operands / f32 accumulate (vocoder)", "data": "synthetic",
-            "config": {"workload": wl["name"], "global_batch": B * world, "seq_len": N, "parallelism": f"utterance-sharded x{world}",
-                       "cond_scale": 0.7, "sm_budget": {"t2s": t2s_sms, "flow+vocoder": flow_sms} if t2s_sms else None, "l2": "working set (0.8 GB weights + 1.2 GB activations) larger than L2; no flush needed"},
-            "clocks": clocks, "gpu_launches": launches * world,
-            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e},
-            "ode_step_ms": ode_step_ms, "roofline": roofline,
-        }
+        line["roofline"] = roofline
         if t2s_info is not None:
             line["t2s"] = t2s_info
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    # free this workload's device memory before the next one is measured in the same process
+    sampler.close()
+    gen.close()
+    if t2s is not None:
+        t2s.close()
+    del sampler, gen, t2s
+    torch.cuda.empty_cache()
     return line
 
 
-def run_vocoder_sweep(args):
-    """BASELINE config C5: HiFi-GAN throughput sweep, mel length x batch; one JSON line per point on rank 0.
-    Traffic model per layer-by-layer execution (what this implementation does): every conv reads its 16-bit input and
-    writes a 16-bit and/or fp32 output (+ fp32 residual read) -- reported as `model_gbs`; FLOPs are algorithmic."""
+def vocoder_traffic_model(B, T, fused_last):
+    """Bytes moved by the layer-by-layer schedule (what the implementation does): every conv reads its 16-bit input and
+    writes a 16-bit and/or fp32 output (+ fp32 residual read); the fused last stage reads its input once (x halo)."""
+    c_pad, t_len, byt = [512, 256, 128, 64, 64], T, 0.0
+    byt += B * T * (80 * 4 + 128 * 2 + 128 * 2 + c_pad[0] * 2)
+    for i, (u, k) in enumerate(zip((5, 4, 4, 2), (8, 8, 4, 4))):
+        t_out = (t_len - 1) * u - 2 * ((k - u) // 2) + k
+        n = B * t_out * c_pad[i + 1]
+        byt += B * t_len * c_pad[i] * 2 + n * 6                      # upsample: read in, write f32 + 16-bit
+        if fused_last and i == 3:
+            byt += B * t_out * (32 * 4 * 382 / 256 + 4)             # stage input once (x halo) + waveform
+        else:
+            byt += 3 * (3 * (n * 2 + n * 2) + 3 * (n * 2 + n * 4 + n * 4 + n * 2))   # 3 resblocks x 3 x (c1: r+w, c2: r + res + w f32 + w h)
+            byt += 3 * n * 4 + n * 2                                  # stage mean
+        t_len = t_out
+    if not fused_last:
+        byt += B * t_len * (64 * 2 * 1 + 4)
+    return byt
+
+
+def run_vocoder_sweep(args, ctx=None, quiet=False):
+    """BASELINE config C5: HiFi-GAN throughput sweep, mel length T in {256, 1024, 4096, 16384} x batch B in {1, 2, 4, 8, 16, 32}
+    (points with B*T > 131072 frames are skipped: they are several copies of a smaller point), on 1 GPU or -- under
+    torchrun -- on every rank at once (weak scaling: each rank runs the same point on its own mels; value = sum over ranks /
+    max-over-ranks time).  One JSON line per point on rank 0 unless `quiet`.  FLOPs are algorithmic (281.3 MFLOP per mel
+    frame); `model_gbs` is a hand traffic model of the schedule, NOT a measurement -- the measured DRAM bytes of the bench
+    shape are in profiles/ (ncu dram__bytes)."""
     import covomix_b200  # noqa: F401
     from covomix_b200 import _native as nat, synthetic as syn
     from covomix_b200.vocoder import B200Generator
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
+    own_ctx = ctx is None
+    if own_ctx:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=dev)
+        ctx = dict(world=world, rank=rank, local=local, dev=dev, dist=dist)
+    world, rank, dev, dist = ctx["world"], ctx["rank"], ctx["dev"], ctx["dist"]
     gen = B200Generator(syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234), syn.HIFIGAN_COVOMIX, dev)
     pk = peaks()
-    g = torch.Generator().manual_seed(5)
+    g = torch.Generator().manual_seed(5 + rank)
+    fused_last = not os.environ.get("COVO_HIFIGAN_NO_FUSED")        # last stage = one tile-resident kernel
     out = []
     for T in (256, 1024, 4096, 16384):
-        for B in (1, 8, 32):
+        for B in (1, 2, 4, 8, 16, 32):
             if B * T > 32 * 4096:
                 continue
             mel = syn.synthetic_logmel(g, B, 80, T).to(dev)
             for _ in range(3):
                 gen(mel)
+            if dist is not None:
+                dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = max(3, args.steps)
@@ -461,34 +550,62 @@ def run_vocoder_sweep(args):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            with nat.profile() as prof:
-                gen(mel)
-            pr = prof.result
-            flops = 281.3e6 * T * B
-            # bytes moved by the layer-by-layer schedule: per output sample-channel of a stage with C padded channels
-            c_pad, t_len, byt = [512, 256, 128, 64, 64], T, 0.0
-            byt += B * T * (80 * 4 + 128 * 2 + 128 * 2 + c_pad[0] * 2)
-            fused_last = not os.environ.get("COVO_HIFIGAN_NO_FUSED")        # last stage = one tile-resident kernel
-            for i, (u, k) in enumerate(zip((5, 4, 4, 2), (8, 8, 4, 4))):
-                t_out = (t_len - 1) * u - 2 * ((k - u) // 2) + k
-                n = B * t_out * c_pad[i + 1]
-                byt += B * t_len * c_pad[i] * 2 + n * 6                      # upsample: read in, write f32 + 16-bit
-                if fused_last and i == 3:
-                    byt += B * t_out * (32 * 4 * 382 / 256 + 4)             # stage input once (x halo) + waveform
-                else:
-                    byt += 3 * (3 * (n * 2 + n * 2) + 3 * (n * 2 + n * 4 + n * 4 + n * 2))   # 3 resblocks x 3 x (c1: r+w, c2: r + res + w f32 + w h)
-                    byt += 3 * n * 4 + n * 2                                  # stage mean
-                t_len = t_out
-            if not fused_last:
-                byt += B * t_len * (64 * 2 * 1 + 4)
-            line = {"metric": "audio-seconds/sec (RTF), HiFi-GAN only", "workload": "C5 vocoder sweep", "T": T, "B": B,
-                    "ms": ms, "value": B * T / FRAME_RATE / (ms * 1e-3), "unit": "audio-s/s",
-                    "achieved_tflops": flops / (ms * 1e-3) / 1e12, "frac_of_tensor_peak": flops / (ms * 1e-3) / 1e12 / pk["tflops"],
-                    "model_gbs": byt / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": byt / (ms * 1e-3) / 1e9 / pk["hbm"],
-                    "kernel_ms": {k: round(v[0], 3) for k, v in pr.items() if v[2]}, "launches": gen.launches_per_forward()}
+            if dist is not None:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            kernel_ms = None
+            if not quiet:
+                with nat.profile() as prof:
+                    gen(mel)
+                kernel_ms = {k: round(v[0], 3) for k, v in prof.result.items() if v[2]}
+            flops = 281.3e6 * T * B * world
+            byt = vocoder_traffic_model(B, T, fused_last) * world
+            line = {"metric": "audio-seconds/sec (RTF), HiFi-GAN only", "workload": "C5 vocoder sweep", "T": T, "B": B, "n_gpus": world,
+                    "ms": ms, "value": world * B * T / FRAME_RATE / (ms * 1e-3), "unit": "audio-s/s",
+                    "achieved_tflops": flops / (ms * 1e-3) / 1e12,
+                    "frac_of_tensor_peak": flops / (ms * 1e-3) / 1e12 / (pk["tflops"] * world),
+                    "model_gbs": byt / (ms * 1e-3) / 1e9, "model_frac_of_hbm_peak": byt / (ms * 1e-3) / 1e9 / (pk["hbm"] * world),
+                    "launches": gen.launches_per_forward()}
+            if kernel_ms is not None:
+                line["kernel_ms"] = kernel_ms
+            if quiet:
+                line = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in line.items()
+                        if k in ("T", "B", "n_gpus", "ms", "value", "achieved_tflops", "frac_of_tensor_peak")}
             out.append(line)
-            print(json.dumps(line), flush=True)
-    return out
+            if rank == 0 and not quiet:
+                print(json.dumps(line), flush=True)
+    gen.close()
+    del gen
+    torch.cuda.empty_cache()
+    if own_ctx and dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out if rank == 0 else None
+
+
+def cpu_c2_measured():
+    """One MEASURED (not extrapolated) end-to-end CPU number: the full BASELINE configs[1] job -- VoSingle, 32 Euler steps
+    (64 network passes), N = 650, B = 1, then the vocoder on the 500 generated frames -- through the oracle port on all
+    host cores.  About 30-40 s."""
+    from covomix_b200 import synthetic as syn
+    from oracle import covomix_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = WORKLOADS["c2"]
+    cfg = syn.VOSINGLE
+    sd = syn.synthetic_flow_state_dict(cfg, 1234)
+    hsd = syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234)
+    _, ids, cond, y0, _ = make_inputs(wl)
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        mel = orc.flow_sample(sd, cfg, ids, cond, y0, cond_scale=0.7, method="euler", step_size=1.0 / wl["n_steps"])
+        t1 = time.perf_counter()
+        orc.hifigan_forward(hsd, syn.HIFIGAN_COVOMIX, mel[:, wl["prompt"]:, :].permute(0, 2, 1).contiguous())
+        t2 = time.perf_counter()
+    audio_s = (wl["N"] - wl["prompt"]) / FRAME_RATE
+    return {"workload": wl["name"], "value": audio_s / (t2 - t0), "unit": "audio-s/s", "seconds": t2 - t0, "flow_seconds": t1 - t0,
+            "vocoder_seconds": t2 - t1, "cores": cores, "kind": "port", "sample": "the whole job, measured once (no extrapolation)"}
 
 
 def cpu_baseline(wl, cfg):
@@ -520,6 +637,7 @@ def cpu_baseline(wl, cfg):
         sec += wl["B"] * wl["t2s"]["steps"] * tt
         extra = f" + {tt * 1e3:.1f} ms per text-to-semantic decoding step (oracle, B = 1, 64 cached positions) x {wl['t2s']['steps']} steps"
     return {"value": wl["B"] * gen_frames / FRAME_RATE / sec, "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "c2_measured": cpu_c2_measured(),
             "sample": f"1 of {wl['B']} items, 1 of {n_eval} CFG velocity evaluations ({tv:.2f} s, fp32 torch CPU) + vocoder on 1 item "
                       f"({th:.2f} s){extra}; extrapolated linearly to the full step",
             "ode_step_ms_b1": tv * 1e3}
@@ -553,6 +671,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS) + ["c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="default workload only: skip the attached C2 / C4-pipelined / C5 measurements (`other_configs`)")
     args = ap.parse_args()
     if args.workload == "c5":
         run_vocoder_sweep(args)

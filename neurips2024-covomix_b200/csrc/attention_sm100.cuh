@@ -145,10 +145,14 @@ __device__ __forceinline__ void exp2_fma2(float& p0, float& p1, float x0, float 
 __device__ __forceinline__ void named_bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
+// The persistent work-item loop, callable from the stand-alone kernel below and from the persistent flow-step kernel
+// (flow_persistent.cuh).  desc: where the TMA descriptor lives (parameter space or global memory); args: the scalar
+// fields (may be a shared-memory copy); smem: 1024-byte aligned, ATT_SMEM_BYTES - 1024 bytes; tmem_base: 512 allocated
+// columns.  Warp roles: 0 TMA, 1 MMA, 4-7 / 8-11 softmax groups A / B; the caller has already applied setmaxnreg
+// (warps 0-3 at 56, warps 4-11 at 224).  Every thread of the CTA must call it.
 template <int POLY_MASK, int HANDOFF = 128>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnArgs args) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnArgs& args, uint8_t* smem, uint32_t tmem_base, int cta,
+                                              int n_ctas) {
     uint8_t* sQ = smem;                                 // 2 buffers x 2 groups
     uint8_t* sK = sQ + 4 * ATT_TILE_BYTES;              // ATT_KS stages
     uint8_t* sV = sK + ATT_KS * ATT_TILE_BYTES;         // ATT_VS stages
@@ -163,14 +167,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     uint64_t* s_free = s_full + 2;                      //             softmax -> MMA : S_g(t) has been pulled into registers
     uint64_t* p_full = s_free + 2;                      //             softmax -> MMA : P_g(t) is in TMEM (and O_g rescaled if needed)
     uint64_t* o_full = p_full + 2;                      //             MMA -> softmax : P_g(t) V(t) done (P consumed, O_g updated)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_kv = (args.N + ATT_BN - 1) / ATT_BN;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&args.tmQKV);
+        tma_prefetch_desc(&desc->tmQKV);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&q_full[i], 1);
             mbar_init(&q_empty[i], 1);
@@ -189,43 +192,35 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         }
         fence_mbar_init();
     }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, ATT_TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S = tmem_base;            // + group * 128
     const uint32_t tmem_O = tmem_base + 256;      // + group * 64
     const uint32_t tmem_P = tmem_base + 384;      // + group * 64: P as bf16 pairs, the A operand of the PV MMA
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && elect_one()) {
             // ===================================================== TMA producer
             int ks = 0, vs = 0;
             uint32_t kph = 0, vph = 0;
             int il = 0;                                        // local work-item counter
-            for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++il) {
+            for (int w = cta; w < args.n_items; w += n_ctas, ++il) {
                 const AttnItem item = attn_decode(args, w);
                 const int qb = il & 1;
                 mbar_wait(&q_empty[qb], ((il >> 1) & 1) ^ 1);
                 mbar_expect_tx(&q_full[qb], (item.two ? 2 : 1) * ATT_TILE_BYTES);
-                tma_load_3d(sQ + (2 * qb) * ATT_TILE_BYTES, &args.tmQKV, &q_full[qb], item.head * ATT_D, item.q0, item.seq);
+                tma_load_3d(sQ + (2 * qb) * ATT_TILE_BYTES, &desc->tmQKV, &q_full[qb], item.head * ATT_D, item.q0, item.seq);
                 if (item.two)
-                    tma_load_3d(sQ + (2 * qb + 1) * ATT_TILE_BYTES, &args.tmQKV, &q_full[qb], item.head * ATT_D, item.q0 + ATT_BG,
+                    tma_load_3d(sQ + (2 * qb + 1) * ATT_TILE_BYTES, &desc->tmQKV, &q_full[qb], item.head * ATT_D, item.q0 + ATT_BG,
                                 item.seq);
                 for (int j = 0; j < n_kv; ++j) {
                     mbar_wait(&k_empty[ks], kph ^ 1);
                     mbar_expect_tx(&k_full[ks], ATT_TILE_BYTES);
-                    tma_load_3d(sK + ks * ATT_TILE_BYTES, &args.tmQKV, &k_full[ks], args.inner + item.head * ATT_D, j * ATT_BN,
+                    tma_load_3d(sK + ks * ATT_TILE_BYTES, &desc->tmQKV, &k_full[ks], args.inner + item.head * ATT_D, j * ATT_BN,
                                 item.seq);
                     if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
                     mbar_wait(&v_empty[vs], vph ^ 1);
                     mbar_expect_tx(&v_full[vs], ATT_TILE_BYTES);
-                    tma_load_3d(sV + vs * ATT_TILE_BYTES, &args.tmQKV, &v_full[vs], 2 * args.inner + item.head * ATT_D,
+                    tma_load_3d(sV + vs * ATT_TILE_BYTES, &desc->tmQKV, &v_full[vs], 2 * args.inner + item.head * ATT_D,
                                 j * ATT_BN, item.seq);
                     if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
                 }
@@ -239,10 +234,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             const uint64_t dK0 = smem_desc_sw128(smem_u32(sK), 1024, 16);
             const uint64_t dV0 = smem_desc_sw128(smem_u32(sV), 1024, ATT_TILE_BYTES);
             int n_my = 0;
-            for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) ++n_my;
+            for (int w = cta; w < args.n_items; w += n_ctas) ++n_my;
             const uint32_t total = static_cast<uint32_t>(n_my) * n_kv;
             // cursor of step u (the S tile) and the descriptors of the two previous steps (their PV products)
-            int il = 0, j = 0, w = blockIdx.x;
+            int il = 0, j = 0, w = cta;
             int two_c = n_my > 0 ? attn_decode(args, w).two : 0;
             int ks = 0;
             uint32_t kph = 0;
@@ -320,13 +315,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 if (have && ++j == n_kv) {
                     j = 0;
                     ++il;
-                    w += gridDim.x;
+                    w += n_ctas;
                     if (w < args.n_items) two_c = attn_decode(args, w).two;
                 }
             }
         }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    } else if (warp < 12) {
         // ===================================================== softmax warpgroups: thread == query row
         const int g = (warp - 4) >> 2;                 // 0: group A (warps 4-7), 1: group B (warps 8-11)
         const int lq = warp & 3;                       // TMEM lane quarter == SM sub-partition of this warp
@@ -340,7 +334,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         uint32_t itp = 0;            // ... of which in pair items (token hand-offs with the other group)
         bool s_ready = false;        // s_full of the coming tile has already been observed complete
 
-        for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+        for (int w = cta; w < args.n_items; w += n_ctas) {
             const AttnItem item = attn_decode(args, w);
             if (g == 1 && !item.two) continue;
             const bool ho = HANDOFF > 0 && args.stagger != 0 && item.two;
@@ -521,6 +515,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         }   // work items
     }
 
+}
+
+template <int POLY_MASK, int HANDOFF = 128>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 1) {
+        tmem_alloc(&tmem_slot, ATT_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    attention_run<POLY_MASK, HANDOFF>(&args, args, smem, tmem_base, blockIdx.x, gridDim.x);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

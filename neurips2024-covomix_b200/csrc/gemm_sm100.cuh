@@ -90,11 +90,18 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b, int is_fp16) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// The persistent tile loop of one GEMM launch, callable from the stand-alone kernel below and from the persistent
+// flow-step kernel (flow_persistent.cuh), which walks a whole list of ops inside one launch.
+//   desc : where the TMA descriptors live (kernel parameter space or global memory -- never shared memory)
+//   args : the scalar fields (may be the same object, or a shared-memory copy of it)
+//   smem : 1024-byte aligned, GemmCfg<BN>::SMEM_BYTES - 1024 bytes;  tmem_base: 2*BN allocated TMEM columns
+//   epi_warp0 : first of the 8 epilogue warps (its TMEM lane quarter is warp % 4 whatever the offset)
+//   cta / n_ctas : this CTA's slot in the persistent schedule
+// Every thread of the CTA must call it (it initialises the mbarriers and synchronises the CTA once).
 template <int BN, int AB_FMT /*0 fp16, 1 bf16*/>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
+__device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& args, uint8_t* smem, uint32_t tmem_base,
+                                         int epi_warp0, int cta, int n_ctas) {
     using Cfg = GemmCfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
     uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_STAGING_BYTES);
@@ -103,7 +110,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     uint64_t* tfull = bars + 2 * Cfg::STAGES;      // [2]
     uint64_t* tempty = bars + 2 * Cfg::STAGES + 2; // [2]
     uint64_t* rbar = bars + 2 * Cfg::STAGES + 4;   // [GEMM_EPI_WARPS] residual sub-tile landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4 + GEMM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -115,8 +121,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int k_iters = args.taps * args.kc_per_tap;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&args.tmA);
-        tma_prefetch_desc(&args.tmB);
+        tma_prefetch_desc(&desc->tmA);
+        tma_prefetch_desc(&desc->tmB);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -128,21 +134,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int w = 0; w < GEMM_EPI_WARPS; ++w) mbar_init(&rbar[w], 1);
         fence_mbar_init();
     }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = cta; tile < total_tiles; tile += n_ctas) {
                 const int n_idx = tile % args.n_tiles;
                 const int mz = tile / args.n_tiles;
                 const int m_idx = mz % m_tiles_per_z;
@@ -157,8 +156,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
                         uint8_t* sb = sa + GEMM_STAGE_A_BYTES;
                         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                        tma_load_3d(sa, &args.tmA, &full[s], kc * GEMM_BK, arow, az);
-                        tma_load_2d(sb, &args.tmB, &full[s], (tap * args.kc_per_tap + kc) * GEMM_BK, n0);
+                        tma_load_3d(sa, &desc->tmA, &full[s], kc * GEMM_BK, arow, az);
+                        tma_load_2d(sb, &desc->tmB, &full[s], (tap * args.kc_per_tap + kc) * GEMM_BK, n0);
                         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                     }
                 }
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = cta; tile < total_tiles; tile += n_ctas) {
                 mbar_wait(&tempty[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -194,10 +193,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
-    } else if (warp - 2 < EPI_WARPS_ACTIVE) {
+    } else if (warp >= epi_warp0 && warp - epi_warp0 < EPI_WARPS_ACTIVE) {
         // ===================================================== epilogue warps
-        // warp e = warp-2: TMEM lane quarter lq = warp % 4 (hardware restriction), column half = e / 4.
-        const int e = warp - 2;
+        // warp e = warp - epi_warp0: TMEM lane quarter lq = warp % 4 (hardware restriction), column half = e / 4.
+        const int e = warp - epi_warp0;
         const int lq = warp & 3;
         const int chalf = e >> 2;
         uint8_t* buf = staging + e * GEMM_EPI_BUF_BYTES;          // [32 rows][128 B]; 16-B chunk c of row r at (c ^ (r&7))*16
@@ -212,7 +211,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         constexpr int NCH = COLS_PER_WARP / 64;
         const bool use_tma = args.scatter == 0;
         const bool has_res = args.has_residual != 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = cta; tile < total_tiles; tile += n_ctas) {
             const int n_idx = tile % args.n_tiles;
             const int mz = tile / args.n_tiles;
             const int m_idx = mz % m_tiles_per_z;
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             if (has_res && rows_live && n0 < args.n_valid && lane == 0) {
                 bulk_wait_read0();
                 mbar_expect_tx(my_rbar, GEMM_EPI_BUF_BYTES);
-                tma_load_3d(buf, &args.tmRes, my_rbar, n0, q_warp0, z);
+                tma_load_3d(buf, &desc->tmRes, my_rbar, n0, q_warp0, z);
             }
 
             mbar_wait(&tfull[as], aph);
@@ -305,12 +304,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                 fence_proxy_async_smem();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    tma_store_3d(&args.tmOutF, buf, ncol, q_warp0, z);
+                                    tma_store_3d(&desc->tmOutF, buf, ncol, q_warp0, z);
                                     bulk_commit();
                                     if (has_res && sp == 0 && ncol + 32 < args.n_valid) {
                                         bulk_wait_read0();
                                         mbar_expect_tx(my_rbar, GEMM_EPI_BUF_BYTES);
-                                        tma_load_3d(buf, &args.tmRes, my_rbar, ncol + 32, q_warp0, z);
+                                        tma_load_3d(buf, &desc->tmRes, my_rbar, ncol + 32, q_warp0, z);
                                     }
                                 }
                             }
@@ -334,7 +333,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_3d(&args.tmOutH, buf, ncol0, q_warp0, z);
+                            tma_store_3d(&desc->tmOutH, buf, ncol0, q_warp0, z);
                             bulk_commit();
                         }
                     }
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     if (has_res && lane == 0 && c + 1 < NCH && ncol0 + 64 < args.n_valid) {
                         bulk_wait_read0();
                         mbar_expect_tx(my_rbar, GEMM_EPI_BUF_BYTES);
-                        tma_load_3d(buf, &args.tmRes, my_rbar, ncol0 + 64, q_warp0, z);
+                        tma_load_3d(buf, &desc->tmRes, my_rbar, ncol0 + 64, q_warp0, z);
                     }
                 } else {
                     // ---------------- scatter path (ConvTranspose1d): smem transpose, lane = column, per-element stores
@@ -384,14 +383,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
-        if (lane == 0) bulk_wait_all();      // smem must stay valid until every bulk store has been read out
+        if (lane == 0) bulk_wait_all();      // smem must stay valid (and the output be complete) when the caller moves on
     }
+}
 
+template <int BN, int AB_FMT /*0 fp16, 1 bf16*/>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 1) {
+        tmem_alloc(&tmem_slot, GemmCfg<BN>::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    gemm_run<BN, AB_FMT>(&args, args, smem, tmem_base, 2, blockIdx.x, gridDim.x);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        tmem_dealloc(tmem_base, GemmCfg<BN>::TMEM_COLS);
     }
 }
 

@@ -44,3 +44,15 @@ def test_workloads_follow_baseline_configs():
         w = b.WORKLOADS[name]
         assert w["t2s"]["steps"] == w["N"] - w["prompt"] == 1500 and w["B"] == 8                           # 64 utterances / 8 GPUs
     assert b.WORKLOADS["c4p"]["t2s_sms"] > 0 and "t2s_sms" not in b.WORKLOADS["c4"]
+
+
+def test_both_arms_report_the_same_config():
+    """The driver compares the `config` objects of the B200 arm and the reference arm (`same_config`)."""
+    b = _bench()
+    for key, wl in b.WORKLOADS.items():
+        t2s_sms = wl.get("t2s_sms", 0)
+        for world in (1, 8):
+            ref = b.config_for(wl, world, t2s_sms, None)                       # run_reference
+            ours = b.config_for(wl, world, t2s_sms, 148 - t2s_sms if t2s_sms else None)   # bench_workload
+            assert ref == ours and ref["workload"] == wl["name"] and ref["global_batch"] == wl["B"] * world
+            assert ("t2s_assumption" in ref) == ("t2s" in wl)
