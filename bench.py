@@ -411,7 +411,7 @@ def bench_workload(args, wl_key, ctx, detail=True):
         e1.record()
         torch.cuda.synchronize()
         ode_step_ms = e0.elapsed_time(e1) / 3
-        launches = (sampler.launches_per_sample(0.7) + gen.launches_per_forward()) * K + (t2s.launches_per_generate() * K if t2s is not None else 0)
+        launches = (sampler.last_launches() + gen.launches_per_forward()) * K + (t2s.launches_per_generate() * K if t2s is not None else 0)
         line = {
             "metric": "audio-seconds/sec (RTF)", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

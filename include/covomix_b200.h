@@ -86,6 +86,11 @@ int covo_flow_velocity(covo_flow* h, const int64_t* ids, const float* cond, cons
 /* Number of kernels one covo_flow_sample call launches for this configuration (bench.py's gpu_launches). */
 int covo_flow_launches_per_sample(const covo_flow* h, int method, int n_steps, float cond_scale);
 
+/* Kernels launched by the most recent covo_flow_sample call on this handle.  Short utterances (2*B*N <= 4096 rows) run
+ * every evaluation and solver update of the call inside ONE persistent cooperative kernel (csrc/flow_persistent.cuh), so
+ * the count is then 9 (the per-call prologue + that kernel) instead of covo_flow_launches_per_sample. */
+int covo_flow_last_launches(const covo_flow* h);
+
 /* ---- HiFi-GAN generator ---------------------------------------------------------------------------
  * Mirrors the fields Generator.__init__ reads from the JSON config (hifi-gan/models.py:76-98,
  * hifi-gan/config_covomix.json). */

@@ -24,7 +24,7 @@ EXPORTS = (
     "covo_t2s_create", "covo_t2s_destroy", "covo_t2s_workspace_bytes", "covo_t2s_generate",
     "covo_t2s_launches_per_generate", "covo_t2s_weight_bytes_per_step",
     "covo_mel_create", "covo_mel_destroy", "covo_mel_frames", "covo_mel_forward",
-    "covo_flow_set_sm_limit", "covo_hifigan_set_sm_limit", "covo_t2s_set_sm_limit", "covo_flow_set_step_size",
+    "covo_flow_set_sm_limit", "covo_hifigan_set_sm_limit", "covo_t2s_set_sm_limit", "covo_flow_set_step_size", "covo_flow_last_launches",
 )
 
 
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
     L.covo_flow_velocity.argtypes = [vp, vp, vp, vp, f32, vp, i32, i32, f32, vp, sz, vp]
     L.covo_flow_launches_per_sample.argtypes = [vp, i32, i32, f32]
     L.covo_flow_set_step_size.argtypes = [vp, f32]
+    L.covo_flow_last_launches.argtypes = [vp]
     L.covo_hifigan_create.argtypes = [C.POINTER(HifiganCfg), vp, sz, i32, C.POINTER(vp)]
     L.covo_hifigan_destroy.argtypes = [vp]
     L.covo_hifigan_workspace_bytes.argtypes = [vp, i32, i32]
@@ -126,7 +127,7 @@ def lib() -> C.CDLL:
 
 
 PROF_CLASSES = ("gemm_tc", "attention_tc", "rmsnorm", "convpos", "elementwise", "prologue", "gemm_tc_vocoder",
-                "t2s_decode")
+                "t2s_decode", "flow_persistent")
 
 
 class profile:

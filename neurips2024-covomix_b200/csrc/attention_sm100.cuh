@@ -100,22 +100,6 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {   // sm_100 
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-// packed fp32 pairs (sm_100 FFMA2 / FADD2): two lanes of one 64-bit register pair per instruction
-__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
 // 2^x for a pair on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x) through the 1.5 * 2^23 trick, 2^f from a
 // degree-3 minimax polynomial on [-0.5, 0.5] (max relative error 7.5e-5), 2^n added into the exponent field.
 // x is clamped at -125 (the result is then ~2e-38 instead of 0 -- masked keys carry -inf).  x <= ~8 by construction.
@@ -148,9 +132,11 @@ __device__ __forceinline__ void named_bar_arrive64(int id) { asm volatile("bar.a
 // The persistent work-item loop, callable from the stand-alone kernel below and from the persistent flow-step kernel
 // (flow_persistent.cuh).  desc: where the TMA descriptor lives (parameter space or global memory); args: the scalar
 // fields (may be a shared-memory copy); smem: 1024-byte aligned, ATT_SMEM_BYTES - 1024 bytes; tmem_base: 512 allocated
-// columns.  Warp roles: 0 TMA, 1 MMA, 4-7 / 8-11 softmax groups A / B; the caller has already applied setmaxnreg
-// (warps 0-3 at 56, warps 4-11 at 224).  Every thread of the CTA must call it.
-template <int POLY_MASK, int HANDOFF = 128>
+// columns.  Warp roles: 0 TMA, 1 MMA, 4-7 / 8-11 softmax groups A / B.  Every thread of the CTA must call it.
+// ROLE: 0 = dispatch on the warp index (stand-alone kernel), 1 = caller is a control warp (0-3), 2 = caller is a softmax warp
+// (4-11) -- the persistent kernel splits its warps once at the top so that ptxas sees each role's register budget.
+// SETREG: apply setmaxnreg here (warps 0-3 -> 56, warps 4-11 -> 224); otherwise the caller has done it.
+template <int POLY_MASK, int HANDOFF = 128, int ROLE = 0, bool SETREG = true>
 __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnArgs& args, uint8_t* smem, uint32_t tmem_base, int cta,
                                               int n_ctas) {
     uint8_t* sQ = smem;                                 // 2 buffers x 2 groups
@@ -167,6 +153,7 @@ __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnAr
     uint64_t* s_free = s_full + 2;                      //             softmax -> MMA : S_g(t) has been pulled into registers
     uint64_t* p_full = s_free + 2;                      //             softmax -> MMA : P_g(t) is in TMEM (and O_g rescaled if needed)
     uint64_t* o_full = p_full + 2;                      //             MMA -> softmax : P_g(t) V(t) done (P consumed, O_g updated)
+    uint64_t* mma_done = o_full + 2;                    // every MMA and commit of this call has completed (barriers may be re-initialised)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -190,6 +177,7 @@ __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnAr
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
         }
+        mbar_init(mma_done, 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -197,7 +185,8 @@ __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnAr
     const uint32_t tmem_O = tmem_base + 256;      // + group * 64
     const uint32_t tmem_P = tmem_base + 384;      // + group * 64: P as bf16 pairs, the A operand of the PV MMA
 
-    if (warp < 4) {
+    if (ROLE != 2 && warp < 4) {
+        if (SETREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && elect_one()) {
             // ===================================================== TMA producer
             int ks = 0, vs = 0;
@@ -319,8 +308,11 @@ __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnAr
                     if (w < args.n_items) two_c = attn_decode(args, w).two;
                 }
             }
+            umma_commit(mma_done);
+            mbar_wait(mma_done, 0);
         }
-    } else if (warp < 12) {
+    } else if (ROLE != 1 && warp >= 4 && warp < 12) {
+        if (SETREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================================================== softmax warpgroups: thread == query row
         const int g = (warp - 4) >> 2;                 // 0: group A (warps 4-7), 1: group B (warps 8-11)
         const int lq = warp & 3;                       // TMEM lane quarter == SM sub-partition of this warp
@@ -531,9 +523,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    attention_run<POLY_MASK, HANDOFF>(&args, args, smem, tmem_base, blockIdx.x, gridDim.x);
+    attention_run<POLY_MASK, HANDOFF, 0, true>(&args, args, smem, tmem_base, blockIdx.x, gridDim.x);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

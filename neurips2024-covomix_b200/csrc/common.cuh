@@ -152,7 +152,7 @@ inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
 // ------------------------------------------------------------------------------------------------ launch profiler
 // Opt-in (covo_prof_begin/_end): brackets every kernel launch with CUDA events on the launching stream so that
 // bench.py can report per-kernel-class time shares and the dominant kernel's achieved FLOP/s.  Off in normal use.
-enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_NORM = 2, PC_CONVPOS = 3, PC_ELEMWISE = 4, PC_PROLOGUE = 5, PC_GEMM_VOC = 6, PC_T2S_DECODE = 7, PC_COUNT = 8 };
+enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_NORM = 2, PC_CONVPOS = 3, PC_ELEMWISE = 4, PC_PROLOGUE = 5, PC_GEMM_VOC = 6, PC_T2S_DECODE = 7, PC_FLOW_PERSISTENT = 8, PC_COUNT = 9 };
 struct ProfRec {
     int cat;
     double flops;
@@ -190,6 +190,7 @@ struct ProfScope {
 struct DeviceInfo {
     int device = 0;
     int num_sms = 148;
+    int gemm_mc = 1;         // 2: GEMMs with >= 2 M tiles run as cluster pairs sharing the weight tile by TMA multicast
 };
 
 struct ASource {             // 16-bit activations [Z][rows][K], K contiguous
@@ -206,6 +207,7 @@ struct GemmOp {
     int bn = 256;
     int fmt = 1;             // 0 fp16, 1 bf16
     int grid = 1;
+    int mc = 1;              // 2: cluster-pair kernel (gemm_tc_pair_kernel), tmB box is (64, bn / 2)
     int cat = PC_GEMM;       // profiler class
     double flops = 0.0;      // algorithmic FLOPs of this launch (real channels only; padding does not count)
 };
@@ -215,6 +217,8 @@ inline int set_gemm_attr() {
     static bool done = false;
     if (!done) {
         COVO_CK(cudaFuncSetAttribute(gemm_tc_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmCfg<BN>::SMEM_BYTES));
+        COVO_CK(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      GemmCfg<BN>::SMEM_BYTES));
         done = true;
     }
@@ -226,7 +230,7 @@ inline int set_gemm_attr() {
 // in profiles/r01_gemm_microbench.txt), so e.g. M = 1300, N = 1024 takes one wave of 88 BN=128 tiles rather than two
 // waves of 176 BN=64 tiles.
 inline int pick_bn(int n_pad, long long m_tiles, int num_sms, int force_bn) {
-    if (force_bn) return force_bn;
+    if (force_bn && n_pad % force_bn == 0) return force_bn;
     const int cands[3] = {256, 128, 64};
     const double cost[3] = {256.0, 128.0 * 1.10, 64.0 * 1.50};
     int best = 0;
@@ -253,6 +257,8 @@ inline int build_gemm(GemmOp& op, const DeviceInfo& di, const ASource& a, int q_
     op.bn = pick_bn(n_pad, m_tiles, di.num_sms, force_bn);
     if (op.bn == 0 || n_pad % op.bn) return fail(COVO_ERR_INVALID, "GEMM N_pad=%d not tileable", n_pad);
     op.fmt = is_fp16 ? 0 : 1;
+    const int m_tiles_z = ceil_div(q_rows, GEMM_BM);
+    op.mc = (di.gemm_mc == 2 && m_tiles_z >= 2 && di.num_sms >= 2) ? 2 : 1;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.rows), static_cast<uint64_t>(a.Z)};
         uint64_t str[2] = {static_cast<uint64_t>(a.row_stride) * 2, static_cast<uint64_t>(a.z_stride) * 2};
@@ -264,7 +270,7 @@ inline int build_gemm(GemmOp& op, const DeviceInfo& di, const ASource& a, int q_
         const int ktot = taps * a.K;
         uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(n_pad)};
         uint64_t str[1] = {static_cast<uint64_t>(ktot) * 2};
-        uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(op.bn)};
+        uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(op.bn / op.mc)};     // pair kernel: each CTA fetches half of the tile
         COVO_TRY(make_tmap(&op.args.tmB, w, 2, dims, str, box, is_fp16));
     }
     op.args.rows = q_rows;
@@ -272,6 +278,12 @@ inline int build_gemm(GemmOp& op, const DeviceInfo& di, const ASource& a, int q_
     op.args.n_tiles = n_pad / op.bn;
     op.args.taps = taps;
     op.args.kc_per_tap = a.K / GEMM_BK;
+    if (op.mc == 2) {
+        const long long pairs = static_cast<long long>(q_Z) * ceil_div(m_tiles_z, 2) * op.args.n_tiles;
+        const long long clusters = di.num_sms / 2;
+        op.grid = 2 * static_cast<int>(pairs < clusters ? pairs : clusters);
+        return COVO_OK;
+    }
     const long long tiles = m_tiles * op.args.n_tiles;
     op.grid = static_cast<int>(tiles < di.num_sms ? tiles : di.num_sms);
     if (op.grid < 1) op.grid = 1;
@@ -321,7 +333,8 @@ inline int launch_gemm(const GemmOp& op, cudaStream_t st) {
 #define COVO_LAUNCH(BN_, F_)                                                                              \
     do {                                                                                                  \
         COVO_TRY((set_gemm_attr<BN_, F_>()));                                                             \
-        gemm_tc_kernel<BN_, F_><<<op.grid, GEMM_THREADS, GemmCfg<BN_>::SMEM_BYTES, st>>>(op.args);        \
+        if (op.mc == 2) gemm_tc_pair_kernel<BN_, F_><<<op.grid, GEMM_THREADS, GemmCfg<BN_>::SMEM_BYTES, st>>>(op.args); \
+        else gemm_tc_kernel<BN_, F_><<<op.grid, GEMM_THREADS, GemmCfg<BN_>::SMEM_BYTES, st>>>(op.args);   \
     } while (0)
     if (op.fmt == 1) {
         if (op.bn == 256) COVO_LAUNCH(256, 1);

@@ -72,6 +72,13 @@ int covo_flow_create(const covo_flow_cfg* cfg, const void* packed_weights, size_
         return rc;
     }
     h->use_graph = !env_flag("COVO_NO_GRAPH");
+    // COVO_GEMM_MC=2: GEMMs run as cluster pairs sharing the weight tile by TMA multicast (gemm_tc_pair_kernel).  Measured
+    // equal to independent CTAs at C3 (596.7 vs 596.0 ms) and slower at C2 (28.4 vs 27.1 ms): the L2 -> SM fabric is not
+    // what binds these GEMMs, so the default stays 1.
+    if (const char* v = getenv("COVO_GEMM_MC")) h->di.gemm_mc = atoi(v) == 2 ? 2 : 1;
+    if (const char* v = getenv("COVO_FLOW_PERSISTENT")) h->persistent_mode = atoi(v);
+    if (const char* v = getenv("COVO_FLOW_PERSISTENT_ROWS")) h->persistent_max_rows = atoi(v);
+    if (const char* v = getenv("COVO_FLOW_PERSISTENT_BN")) h->persistent_bn = atoi(v);
     h->naive_attn = env_flag("COVO_DEBUG_NAIVE_ATTN");
     *out = h;
     return COVO_OK;
@@ -116,6 +123,8 @@ int covo_flow_launches_per_sample(const covo_flow* h, int method, int n_steps, f
     return 7 + 1 + nfe * (per_net + 1);
 }
 
+int covo_flow_last_launches(const covo_flow* h) { return h ? h->last_launches : 0; }
+
 int covo_flow_sample(covo_flow* h, const int64_t* ids, const float* cond, const float* y0, float* out, int B, int N,
                      int method, int n_steps, float cond_scale, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !ids || !cond || !y0 || !out) return fail(COVO_ERR_INVALID, "null argument");
@@ -135,6 +144,7 @@ int covo_flow_sample(covo_flow* h, const int64_t* ids, const float* cond, const 
         COVO_TRY(flow_enqueue_sample(h, *p, st, &launches));
         p->launches = launches;
     }
+    h->last_launches = p->launches;
     COVO_CK(cudaMemcpyAsync(out, p->x_state, bn * c.dim_x * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return COVO_OK;
 }
@@ -577,6 +587,7 @@ int covo_dbg_gemm(const void* A_bf16, const void* W_bf16, const float* bias, con
     DeviceInfo di;
     COVO_TRY(dbg_device(&di));
     if (N % 64 || K % 64) return fail(COVO_ERR_INVALID, "dbg_gemm needs N, K multiples of 64");
+    if (const char* v = getenv("COVO_GEMM_MC")) di.gemm_mc = atoi(v) == 2 ? 2 : 1;
     GemmOp op;
     gemm_defaults(op.args);
     COVO_TRY(build_gemm(op, di, a2d(A_bf16, K, M), M, 1, W_bf16, N, 1, 0, force_bn));

@@ -2,6 +2,7 @@
 // ConditionalFlowMatcherWrapper.sample / CoVoMix.forward_with_cond_scale (covomix/covomix_model/acoustic.py).
 #pragma once
 #include "common.cuh"
+#include "flow_persistent.cuh"
 
 namespace covo {
 
@@ -43,6 +44,13 @@ struct FlowPlan {
     AttnArgs attn;
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
+    // persistent flow-step kernel (flow_persistent.cuh): op list of one evaluation + per-evaluation solver table, owned by the plan
+    bool persistent = false;
+    MegaOp* d_ops = nullptr;
+    EvalEntry* d_evals = nullptr;
+    unsigned* d_sync = nullptr;      // [0] grid barrier counter, [1] abort flag
+    int n_ops = 0;
+    double flops_per_eval = 0.0;
 };
 
 }  // namespace covo
@@ -62,6 +70,10 @@ struct covo_flow {
     cudaStream_t capture_stream = nullptr;
     bool use_graph = true;
     bool naive_attn = false;
+    int last_launches = 0;         // kernels launched by the most recent covo_flow_sample call
+    int persistent_mode = 0;       // COVO_FLOW_PERSISTENT: 0 (default) never, 1 whenever supported, -1 for M <= persistent_max_rows
+    int persistent_max_rows = 4096;
+    int persistent_bn = 0;         // COVO_FLOW_PERSISTENT_BN: force the GEMM tile width of the persistent path (0: heuristic)
     float step_size = 0.f;         // covo_flow_set_step_size: torchdiffeq grid k*h with the last point snapped to 1
 };
 
@@ -175,6 +187,7 @@ inline ASource a2d(const void* ptr, int K, int rows) {
 inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
     const covo_flow_cfg& c = h->cfg;
     const int D = c.dim, inner = c.heads * c.dim_head, M = p.M, half = c.depth / 2;
+    const int fbn = p.persistent ? h->persistent_bn : 0;       // tile-width override of the persistent path (experiments)
     // per-call constant part of to_embed:  e_const = [emb | cond] W_pc^T + b
     gemm_defaults(p.op_const.args);
     COVO_TRY(build_gemm(p.op_const, h->di, a2d(p.a_pc, h->kpc, M), M, 1, h->embed_wpc.ptr, D, 1, 0));
@@ -183,7 +196,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
     p.op_const.flops = 2.0 * M * D * (c.n_streams * c.dim_phoneme_emb + c.dim_in);
     // per-evaluation part: h0 = x W_x^T + e_const
     gemm_defaults(p.op_embed.args);
-    COVO_TRY(build_gemm(p.op_embed, h->di, a2d(p.xin, h->ldx, M), M, 1, h->embed_wx.ptr, D, 1, 0));
+    COVO_TRY(build_gemm(p.op_embed, h->di, a2d(p.xin, h->ldx, M), M, 1, h->embed_wx.ptr, D, 1, 0, fbn));
     COVO_TRY(gemm_set_outputs(p.op_embed, p.h0, p.e_const, nullptr, D, M, 1, D, 0, 0));
     p.op_embed.flops = 2.0 * M * D * c.dim_x;
 
@@ -205,7 +218,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             a.Z = half + 1;
             a.row_stride = D;
             a.z_stride = static_cast<long long>(M) * D;
-            COVO_TRY(build_gemm(op, h->di, a, M, 1, lw.skip_w.ptr, D, 2, 0));
+            COVO_TRY(build_gemm(op, h->di, a, M, 1, lw.skip_w.ptr, D, 2, 0, fbn));
             op.args.tap_row[0] = op.args.tap_row[1] = 0;
             op.args.tap_z[0] = half;                    // current x
             op.args.tap_z[1] = c.depth - 1 - L;         // LIFO pop (acoustic.py:306-310)
@@ -216,7 +229,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
         {
             GemmOp& op = p.op_qkv[L];
             gemm_defaults(op.args);
-            COVO_TRY(build_gemm(op, h->di, a2d(p.a_norm, D, M), M, 1, lw.qkv_w.ptr, 3 * inner, 1, 0));
+            COVO_TRY(build_gemm(op, h->di, a2d(p.a_norm, D, M), M, 1, lw.qkv_w.ptr, 3 * inner, 1, 0, fbn));
             COVO_TRY(gemm_set_outputs(op, nullptr, nullptr, p.qkv, 3 * inner, M, 1, 3 * inner, 0, 0));
             op.args.rope = p.rope;
             op.args.rope_seq = p.N;
@@ -226,14 +239,14 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
         {
             GemmOp& op = p.op_out[L];
             gemm_defaults(op.args);
-            COVO_TRY(build_gemm(op, h->di, a2d(p.attn_o, inner, M), M, 1, lw.out_w.ptr, D, 1, 0));
+            COVO_TRY(build_gemm(op, h->di, a2d(p.attn_o, inner, M), M, 1, lw.out_w.ptr, D, 1, 0, fbn));
             COVO_TRY(gemm_set_outputs(op, p.x, p.x, nullptr, D, M, 1, D, 0, 0));
             op.flops = 2.0 * M * D * inner;
         }
         {
             GemmOp& op = p.op_ff1[L];
             gemm_defaults(op.args);
-            COVO_TRY(build_gemm(op, h->di, a2d(p.a_norm, D, M), M, 1, lw.ff1_w.ptr, D * c.ff_mult, 1, 0));
+            COVO_TRY(build_gemm(op, h->di, a2d(p.a_norm, D, M), M, 1, lw.ff1_w.ptr, D * c.ff_mult, 1, 0, fbn));
             COVO_TRY(gemm_set_outputs(op, nullptr, nullptr, p.ffh, D * c.ff_mult, M, 1, D * c.ff_mult, 0, 0));
             op.args.bias = lw.ff1_b.as<float>();
             op.args.act_h = ACT_GELU;
@@ -242,7 +255,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
         {
             GemmOp& op = p.op_ff2[L];
             gemm_defaults(op.args);
-            COVO_TRY(build_gemm(op, h->di, a2d(p.ffh, D * c.ff_mult, M), M, 1, lw.ff2_w.ptr, D, 1, 0));
+            COVO_TRY(build_gemm(op, h->di, a2d(p.ffh, D * c.ff_mult, M), M, 1, lw.ff2_w.ptr, D, 1, 0, fbn));
             // bf16 copy of the next layer's input: a skip slot (first half) or the "current" slot (second half)
             __nv_bfloat16* next_h = nullptr;
             if (L + 1 < c.depth) {
@@ -255,7 +268,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
         }
     }
     gemm_defaults(p.op_pred.args);
-    COVO_TRY(build_gemm(p.op_pred, h->di, a2d(p.a_norm, D, M), M, 1, h->pred_w.ptr, h->npred, 1, 0));
+    COVO_TRY(build_gemm(p.op_pred, h->di, a2d(p.a_norm, D, M), M, 1, h->pred_w.ptr, h->npred, 1, 0, fbn));
     COVO_TRY(gemm_set_outputs(p.op_pred, p.vpred, nullptr, nullptr, c.dim_x, M, 1, c.dim_x, 0, 0));
     p.op_pred.flops = 2.0 * M * D * c.dim_x;
 
@@ -362,6 +375,8 @@ inline int flow_enqueue_network(covo_flow* h, FlowPlan& p, int t_idx, cudaStream
     return COVO_OK;
 }
 
+inline int flow_launch_persistent(covo_flow* h, FlowPlan& p, cudaStream_t st);
+
 inline int flow_enqueue_sample(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
     const covo_flow_cfg& c = h->cfg;
     const int n_el = p.BN * h->ldx;                 // the element-wise kernels also rewrite the padding columns of xin
@@ -372,6 +387,11 @@ inline int flow_enqueue_sample(covo_flow* h, FlowPlan& p, cudaStream_t st, int* 
         state_to_input_kernel<<<eb, 256, 0, st>>>(p.x_state, p.xin, p.BN, c.dim_x, h->ldx, p.two_branch);
     }
     ++*launches;
+    if (p.persistent) {
+        COVO_TRY(flow_launch_persistent(h, p, st));      // every evaluation + solver update of the call: one launch
+        ++*launches;
+        return COVO_OK;
+    }
     int ti = 0;
     for (int k = 0; k < p.n_steps; ++k) {
         if (p.method == COVO_ODE_MIDPOINT) {
@@ -431,7 +451,171 @@ inline int flow_enqueue_velocity(covo_flow* h, FlowPlan& p, cudaStream_t st, int
 
 inline void flow_free_plan(FlowPlan* p) {
     if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->d_ops) cudaFree(p->d_ops);
+    if (p->d_evals) cudaFree(p->d_evals);
+    if (p->d_sync) cudaFree(p->d_sync);
     delete p;
+}
+
+inline bool flow_persistent_eligible(const covo_flow* h, const FlowPlan& p) {
+    if (h->naive_attn || p.single_eval || h->cfg.dim != 1024 || h->cfg.conv_pos_kernel != 31) return false;
+    if (h->persistent_mode == 0) return false;
+    if (h->persistent_mode == 1) return true;
+    return p.M <= h->persistent_max_rows;
+}
+
+// Op list of one network evaluation (the launch sequence of flow_enqueue_network + the CFG / solver update) and the
+// solver table, copied to plan-owned device memory.
+inline int flow_build_persistent(covo_flow* h, FlowPlan& p) {
+    const covo_flow_cfg& c = h->cfg;
+    const int D = c.dim, M = p.M, half = c.depth / 2;
+    std::vector<MegaOp> ops;
+    double flops = 0.0;
+    auto gemm = [&](const GemmOp& g) {
+        MegaOp m;
+        memset(&m, 0, sizeof(m));
+        m.type = MOP_GEMM;
+        m.bn = g.bn;
+        m.g = g.args;
+        ops.push_back(m);
+        flops += g.flops;
+    };
+    auto norm = [&](const float* gamma, const float* beta, long long stride) {
+        MegaOp m;
+        memset(&m, 0, sizeof(m));
+        m.type = MOP_NORM;
+        m.n.x = p.x;
+        m.n.gamma = gamma;
+        m.n.beta = beta;
+        m.n.out = p.a_norm;
+        m.n.M = M;
+        m.n.gb_stride = stride;
+        ops.push_back(m);
+    };
+    gemm(p.op_embed);
+    {
+        MegaOp m;
+        memset(&m, 0, sizeof(m));
+        m.type = MOP_CONVPOS;
+        m.c.h = p.h0;
+        m.c.wT = h->conv_wT.as<float>();
+        m.c.bias = h->conv_b.as<float>();
+        m.c.x = p.x;
+        m.c.x_h = p.slots;
+        m.c.N = p.N;
+        m.c.D = D;
+        m.c.Bt = M / p.N;
+        ops.push_back(m);
+    }
+    const long long gb_stride = static_cast<long long>(c.depth) * 4 * D;
+    for (int L = 0; L < c.depth; ++L) {
+        const float* gbl = p.gb + static_cast<size_t>(L) * 4 * D;
+        if (L >= half) gemm(p.op_skip[L]);
+        norm(gbl, gbl + D, gb_stride);
+        gemm(p.op_qkv[L]);
+        {
+            MegaOp m;
+            memset(&m, 0, sizeof(m));
+            m.type = MOP_ATTN;
+            m.a = p.attn;
+            ops.push_back(m);
+            flops += 4.0 * p.N * static_cast<double>(p.N) * c.dim_head * c.heads * (M / p.N);
+        }
+        gemm(p.op_out[L]);
+        norm(gbl + 2 * D, gbl + 3 * D, gb_stride);
+        gemm(p.op_ff1[L]);
+        gemm(p.op_ff2[L]);
+    }
+    norm(h->final_gamma.as<float>(), nullptr, 0);
+    gemm(p.op_pred);
+    {
+        MegaOp m;
+        memset(&m, 0, sizeof(m));
+        m.type = MOP_CFG;
+        m.f.vpred = p.vpred;
+        m.f.x_state = p.x_state;
+        m.f.xin = p.xin;
+        m.f.BN = p.BN;
+        m.f.dx = c.dim_x;
+        m.f.ldx = h->ldx;
+        m.f.s = p.cond_scale;
+        m.f.two_branch = p.two_branch;
+        ops.push_back(m);
+    }
+    std::vector<EvalEntry> evals(p.n_t);
+    for (int e = 0; e < p.n_t; ++e) {
+        if (p.method == COVO_ODE_MIDPOINT) {
+            evals[e].coef = (e & 1) ? p.dts[e] : 0.5f * p.dts[e];     // y_mid = y0 + f0 dt/2 ; y1 = y0 + dt f(t0 + dt/2, y_mid)
+            evals[e].write_state = e & 1;
+        } else {
+            evals[e].coef = p.dts[e];
+            evals[e].write_state = 1;
+        }
+    }
+    p.n_ops = static_cast<int>(ops.size());
+    p.flops_per_eval = flops;
+    COVO_CK(cudaMalloc(&p.d_ops, ops.size() * sizeof(MegaOp)));
+    COVO_CK(cudaMalloc(&p.d_evals, evals.size() * sizeof(EvalEntry)));
+    COVO_CK(cudaMalloc(&p.d_sync, 32768));
+    COVO_CK(cudaMemcpy(p.d_ops, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
+    COVO_CK(cudaMemcpy(p.d_evals, evals.data(), evals.size() * sizeof(EvalEntry), cudaMemcpyHostToDevice));
+    return COVO_OK;
+}
+
+inline int flow_launch_persistent(covo_flow* h, FlowPlan& p, cudaStream_t st) {
+    auto kern = flow_persistent_kernel<0x88, 8>;
+    static bool attr = false;
+    if (!attr) {
+        COVO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
+        int per_sm = 0;
+        COVO_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MEGA_THREADS, MEGA_SMEM_BYTES));
+        if (per_sm < 1) return fail(COVO_ERR_INVALID, "persistent flow kernel does not fit on an SM");
+        attr = true;
+    }
+    COVO_CK(cudaMemsetAsync(p.d_sync, 0, 32768, st));
+    const bool trace = getenv("COVO_FLOW_TRACE") != nullptr && p.n_ops <= 480;
+    MegaArgs a;
+    a.trace = trace ? reinterpret_cast<long long*>(p.d_sync + 64) : nullptr;
+    a.ops = p.d_ops;
+    a.n_ops = p.n_ops;
+    a.evals = p.d_evals;
+    a.n_evals = p.n_t;
+    a.barrier = p.d_sync;
+    a.abort_flag = reinterpret_cast<int*>(p.d_sync + 1);
+    void* params[1] = {&a};
+    ProfScope ps(PC_FLOW_PERSISTENT, p.flops_per_eval * p.n_t, st);
+    if (trace) {
+        long long* gt = reinterpret_cast<long long*>(p.d_sync + 2048);      // internal timelines of the first 200 gemm ops
+        const int zero = 0;
+        COVO_CK(cudaMemcpyToSymbolAsync(g_gemm_trace, &gt, sizeof(gt), 0, cudaMemcpyHostToDevice, st));
+        COVO_CK(cudaMemcpyToSymbolAsync(g_gemm_trace_n, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, st));
+    }
+    COVO_CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(h->di.num_sms), dim3(MEGA_THREADS), params,
+                                        MEGA_SMEM_BYTES, st));
+    if (trace) {                // debug only: synchronises and prints CTA 0's per-op timeline of evaluation 1
+        std::vector<long long> t(2 * p.n_ops);
+        std::vector<MegaOp> ops(p.n_ops);
+        COVO_CK(cudaStreamSynchronize(st));
+        COVO_CK(cudaMemcpy(t.data(), p.d_sync + 64, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        COVO_CK(cudaMemcpy(ops.data(), p.d_ops, ops.size() * sizeof(MegaOp), cudaMemcpyDeviceToHost));
+        static const char* nm[5] = {"gemm", "attn", "norm", "convpos", "cfg"};
+        for (int i = 1; i < p.n_ops; ++i)
+            fprintf(stderr, "[flow trace] op %2d %-7s bn=%3d tiles=%4d: work %6lld cycles, barrier %6lld\n", i, nm[ops[i].type], ops[i].bn,
+                    ops[i].type == MOP_GEMM ? ops[i].g.Z * ((ops[i].g.rows + 127) / 128) * ops[i].g.n_tiles : 0, t[2 * i] - t[2 * i - 1],
+                    t[2 * i + 1] - t[2 * i]);
+        fprintf(stderr, "[flow trace] evaluation 1: %lld cycles for ops 1..%d\n", t[2 * p.n_ops - 1] - t[1], p.n_ops - 1);
+        std::vector<long long> g(8 * 200);
+        COVO_CK(cudaMemcpy(g.data(), p.d_sync + 2048, g.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const int per_eval = 5 * h->cfg.depth + h->cfg.depth / 2 + 2;
+        for (int k = per_eval; k < 2 * per_eval && k < 200; ++k) {        // the gemm ops of evaluation 1
+            const long long* r = g.data() + 8 * k;
+            fprintf(stderr, "[flow trace] gemm #%2d: init %5lld | first stage landed +%5lld | last MMA issued +%6lld | accumulator complete +%5lld | "
+                    "stores issued +%5lld | stores complete +%5lld\n", k - per_eval, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5]);
+        }
+        long long* null_ptr = nullptr;
+        COVO_CK(cudaMemcpyToSymbol(g_gemm_trace, &null_ptr, sizeof(null_ptr)));
+    }
+    return COVO_OK;
 }
 
 // Finds or builds the plan for this call shape.  single_eval: covo_flow_velocity (no graph; t varies per call).
@@ -471,7 +655,11 @@ inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, fl
         delete p;
         return fail(COVO_ERR_INVALID, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     }
+    p->persistent = flow_persistent_eligible(h, *p);
+    const int saved_mc = h->di.gemm_mc;
+    if (p->persistent) h->di.gemm_mc = 1;          // the cooperative kernel is not launched in clusters
     int rc = flow_build_ops(h, *p);
+    h->di.gemm_mc = saved_mc;
     if (rc != COVO_OK) {
         delete p;
         return rc;
@@ -479,7 +667,14 @@ inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, fl
     // padding columns of the bf16 operands (a_pc, xin) must be exact zeros (they meet zero weight columns, but
     // 0 * NaN != 0): embed_input_kernel / state_to_input_kernel / cfg_update_kernel rewrite them on EVERY call, so a
     // cached plan stays valid when the caller reuses or re-allocates the workspace between calls.
-    if (!single_eval && h->use_graph) {
+    if (p->persistent) {
+        rc = flow_build_persistent(h, *p);
+        if (rc != COVO_OK) {
+            flow_free_plan(p);
+            return rc;
+        }
+    }
+    if (!single_eval && h->use_graph && !p->persistent) {
         cudaGraph_t graph = nullptr;
         int launches = 0;
         COVO_CK(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));

@@ -72,6 +72,13 @@ struct GemmArgs {
     void* out_h;
 };
 
+// Debug timeline of gemm_run (CTA 0 only; null in production): [0] entry, [1] barriers initialised, [2] first stage landed,
+// [3] last MMA issued, [4] accumulator of the last tile complete (epilogue warp 0), [5] its stores issued, [6] stores complete
+// (one 8-slot record per gemm_run call, first 200 calls)
+__device__ long long* g_gemm_trace = nullptr;
+__device__ int g_gemm_trace_n = 0;
+#define GTR(slot) do { if (g_gemm_trace != nullptr && blockIdx.x == 0 && gtr_base >= 0) g_gemm_trace[gtr_base + (slot)] = clock64(); } while (0)
+
 template <int BN>
 struct GemmCfg {
     static constexpr int STAGE_B_BYTES = BN * GEMM_BK * 2;
@@ -98,7 +105,14 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b, int is_fp16) {
 //   epi_warp0 : first of the 8 epilogue warps (its TMEM lane quarter is warp % 4 whatever the offset)
 //   cta / n_ctas : this CTA's slot in the persistent schedule
 // Every thread of the CTA must call it (it initialises the mbarriers and synchronises the CTA once).
-template <int BN, int AB_FMT /*0 fp16, 1 bf16*/>
+// ROLE: 0 = dispatch on the warp index; 1 = the caller is a control warp (TMA / MMA); 2 = the caller is an epilogue warp.
+// MC: 1 = independent CTAs.  2 = the CTA is one of a cluster pair (launch with cluster dims (2,1,1)): the pair works on two
+//     vertically adjacent M tiles of the same N tile and SHARES the weight tile -- each CTA fetches half of it and
+//     multicasts that half into both CTAs' shared memory, so the W operand crosses the L2 -> SM fabric once per pair
+//     (the K loop of a 128 x 256 tile asks the fabric for 96 B/clk/SM; chip-wide that is more than L2 delivers).
+//     tmB's box is then (64, BN/2).  A stage may only be refilled when BOTH CTAs' MMAs have read it: every MMA commit on
+//     empty[] is multicast to the pair (count 2).
+template <int BN, int AB_FMT /*0 fp16, 1 bf16*/, int ROLE = 0, int MC = 1>
 __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& args, uint8_t* smem, uint32_t tmem_base,
                                          int epi_warp0, int cta, int n_ctas) {
     using Cfg = GemmCfg<BN>;
@@ -116,16 +130,33 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
     // BN = 64: one 64-column chunk per lane quarter -> only 4 of the 8 epilogue warps have work
     constexpr int EPI_WARPS_ACTIVE = (BN >= 128) ? GEMM_EPI_WARPS : 4;
 
-    const int m_tiles_per_z = (args.rows + GEMM_BM - 1) / GEMM_BM;
+    // MC == 2: the schedule runs over PAIR tiles (two M tiles x one N tile); `cta` / `n_ctas` then count clusters, and
+    // m_tiles_per_z counts pairs (an odd tail pair has a phantom second tile: TMA zero-fills it, nothing is stored)
+    const int crank = MC == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+    if (MC == 2) {
+        cta >>= 1;
+        n_ctas >>= 1;
+    }
+    const int m_tiles_per_z = ((args.rows + GEMM_BM - 1) / GEMM_BM + MC - 1) / MC;
     const int total_tiles = args.Z * m_tiles_per_z * args.n_tiles;
     const int k_iters = args.taps * args.kc_per_tap;
 
+    volatile int& s_gtr_base = *reinterpret_cast<volatile int*>(bars + 48);     // debug slot inside the 512-byte barrier region
+    if (threadIdx.x == 0) {
+        int b = -1;
+        if (g_gemm_trace != nullptr && blockIdx.x == 0) {
+            b = g_gemm_trace_n++;
+            b = b < 200 ? 8 * b : -1;
+        }
+        s_gtr_base = b;
+        if (b >= 0) g_gemm_trace[b] = clock64();
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&desc->tmA);
         tma_prefetch_desc(&desc->tmB);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], MC);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
@@ -134,9 +165,12 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
         for (int w = 0; w < GEMM_EPI_WARPS; ++w) mbar_init(&rbar[w], 1);
         fence_mbar_init();
     }
-    __syncthreads();
+    if (MC == 2) cluster_sync_all();        // the peer's multicast may signal this CTA's barriers from now on
+    else __syncthreads();
+    const int gtr_base = s_gtr_base;
+    if (threadIdx.x == 0) GTR(1);
 
-    if (warp == 0) {
+    if (ROLE != 2 && warp == 0) {
         // ===================================================== TMA producer
         if (elect_one()) {
             int s = 0;
@@ -144,7 +178,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
             for (int tile = cta; tile < total_tiles; tile += n_ctas) {
                 const int n_idx = tile % args.n_tiles;
                 const int mz = tile / args.n_tiles;
-                const int m_idx = mz % m_tiles_per_z;
+                const int m_idx = (mz % m_tiles_per_z) * MC + crank;
                 const int z = mz / m_tiles_per_z;
                 const int q0 = m_idx * GEMM_BM;
                 const int n0 = n_idx * BN;
@@ -157,13 +191,17 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                         uint8_t* sb = sa + GEMM_STAGE_A_BYTES;
                         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
                         tma_load_3d(sa, &desc->tmA, &full[s], kc * GEMM_BK, arow, az);
-                        tma_load_2d(sb, &desc->tmB, &full[s], (tap * args.kc_per_tap + kc) * GEMM_BK, n0);
+                        if (MC == 2)        // this CTA's half of the weight tile, into both CTAs of the pair
+                            tma_load_2d_mc(sb + crank * (Cfg::STAGE_B_BYTES / 2), &desc->tmB, &full[s],
+                                           (tap * args.kc_per_tap + kc) * GEMM_BK, n0 + crank * (BN / 2), 0x3);
+                        else
+                            tma_load_2d(sb, &desc->tmB, &full[s], (tap * args.kc_per_tap + kc) * GEMM_BK, n0);
                         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (ROLE != 2 && warp == 1) {
         // ===================================================== MMA issuer (elect.sync: ptxas keeps operands in uniform registers)
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, AB_FMT, 0, 0);
@@ -180,20 +218,23 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
                 for (int it = 0; it < k_iters; ++it) {
                     mbar_wait(&full[s], ph);
+                    if (it == 0 && tile == cta) GTR(2);
                     tc_fence_after();
                     const uint64_t da = desc_advance(dA0, s * Cfg::STAGE_BYTES);
                     const uint64_t db = desc_advance(dB0, s * Cfg::STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k)
                         umma_f16(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (it | k) != 0);
-                    umma_commit(&empty[s]);
+                    if (MC == 2) umma_commit_mc(&empty[s], 0x3);
+                    else umma_commit(&empty[s]);
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull[as]);
+                GTR(3);
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
-    } else if (warp >= epi_warp0 && warp - epi_warp0 < EPI_WARPS_ACTIVE) {
+    } else if (ROLE != 1 && warp >= epi_warp0 && warp - epi_warp0 < EPI_WARPS_ACTIVE) {
         // ===================================================== epilogue warps
         // warp e = warp - epi_warp0: TMEM lane quarter lq = warp % 4 (hardware restriction), column half = e / 4.
         const int e = warp - epi_warp0;
@@ -214,7 +255,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
         for (int tile = cta; tile < total_tiles; tile += n_ctas) {
             const int n_idx = tile % args.n_tiles;
             const int mz = tile / args.n_tiles;
-            const int m_idx = mz % m_tiles_per_z;
+            const int m_idx = (mz % m_tiles_per_z) * MC + crank;
             const int z = mz / m_tiles_per_z;
             const int q_warp0 = m_idx * GEMM_BM + lq * 32;
             const int n0 = n_idx * BN + chalf * COLS_PER_WARP;
@@ -227,7 +268,19 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                 tma_load_3d(buf, &desc->tmRes, my_rbar, n0, q_warp0, z);
             }
 
+            // RoPE factors of this thread's row: the same 32 (cos, sin) pairs serve every head of the tile, and the row is known
+            // before the accumulator is -- 16 independent 16-byte loads issued under the tail of the MMAs (per-chunk 8-byte
+            // loads after the accumulator arrived cost 22k cycles per tile on the epilogue's critical path)
+            float4 cs4[16];
+            const bool use_rope = args.rope != nullptr && n0 < args.rope_cols && rows_live;
+            if (use_rope) {
+                const int pos = (q_warp0 + lane) % args.rope_seq;
+                const float4* tab = reinterpret_cast<const float4*>(args.rope + static_cast<size_t>(pos) * 32);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cs4[j] = __ldg(tab + j);
+            }
             mbar_wait(&tfull[as], aph);
+            if (e == 0 && lane == 0) GTR(4);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + static_cast<uint32_t>(as * BN + chalf * COLS_PER_WARP) +
                                    (static_cast<uint32_t>(lq * 32) << 16);
@@ -250,16 +303,16 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                 }
                 const int ncol0 = n0 + c * 64;
                 if (!rows_live || ncol0 >= args.n_valid) continue;
-                if (args.rope != nullptr && ncol0 < args.rope_cols) {
-                    const int pos = (q_warp0 + lane) % args.rope_seq;
-                    const float2* tab = args.rope + static_cast<size_t>(pos) * 32;
+                if (use_rope && ncol0 < args.rope_cols) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float2 cs = __ldg(tab + j);
-                        const float x1 = __uint_as_float(r[j]);
-                        const float x2 = __uint_as_float(r[j + 32]);
-                        r[j] = __float_as_uint(x1 * cs.x - x2 * cs.y);
-                        r[j + 32] = __float_as_uint(x2 * cs.x + x1 * cs.y);
+                    for (int j = 0; j < 32; j += 2) {
+                        const float4 cs = cs4[j >> 1];       // (cos_j, sin_j, cos_j+1, sin_j+1)
+                        const float a1 = __uint_as_float(r[j]), a2 = __uint_as_float(r[j + 32]);
+                        const float b1 = __uint_as_float(r[j + 1]), b2 = __uint_as_float(r[j + 33]);
+                        r[j] = __float_as_uint(a1 * cs.x - a2 * cs.y);
+                        r[j + 32] = __float_as_uint(a2 * cs.x + a1 * cs.y);
+                        r[j + 1] = __float_as_uint(b1 * cs.z - b2 * cs.w);
+                        r[j + 33] = __float_as_uint(b2 * cs.z + b1 * cs.w);
                     }
                 }
                 if (args.bias != nullptr) {
@@ -267,10 +320,13 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float4 b = __ldg(b4 + j);
-                        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + b.x);
-                        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y);
-                        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z);
-                        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w);
+                        float s0, s1, s2, s3;
+                        add2(s0, s1, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b.x, b.y);
+                        add2(s2, s3, __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b.z, b.w);
+                        r[4 * j] = __float_as_uint(s0);
+                        r[4 * j + 1] = __float_as_uint(s1);
+                        r[4 * j + 2] = __float_as_uint(s2);
+                        r[4 * j + 3] = __float_as_uint(s3);
                     }
                 }
                 if (use_tma) {
@@ -287,10 +343,13 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                                     for (int c4 = 0; c4 < 8; ++c4) {
                                         const float4 v = lds128f(my_row_s + ((c4 ^ sw) << 4));
                                         const int b = sp * 32 + 4 * c4;
-                                        r[b] = __float_as_uint(__uint_as_float(r[b]) + v.x);
-                                        r[b + 1] = __float_as_uint(__uint_as_float(r[b + 1]) + v.y);
-                                        r[b + 2] = __float_as_uint(__uint_as_float(r[b + 2]) + v.z);
-                                        r[b + 3] = __float_as_uint(__uint_as_float(r[b + 3]) + v.w);
+                                        float s0, s1, s2, s3;
+                                        add2(s0, s1, __uint_as_float(r[b]), __uint_as_float(r[b + 1]), v.x, v.y);
+                                        add2(s2, s3, __uint_as_float(r[b + 2]), __uint_as_float(r[b + 3]), v.z, v.w);
+                                        r[b] = __float_as_uint(s0);
+                                        r[b + 1] = __float_as_uint(s1);
+                                        r[b + 2] = __float_as_uint(s2);
+                                        r[b + 3] = __float_as_uint(s3);
                                     }
                                 } else if (lane == 0) {
                                     bulk_wait_read0();              // previous TMA store has finished reading the buffer
@@ -321,7 +380,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float o0 = __uint_as_float(r[2 * j]), o1 = __uint_as_float(r[2 * j + 1]);
-                            if (args.act_h == ACT_GELU) { o0 = gelu_fast(o0); o1 = gelu_fast(o1); }
+                            if (args.act_h == ACT_GELU) gelu_fast2(o0, o1, o0, o1);
                             else if (args.act_h == ACT_LRELU) { o0 = lrelu(o0, args.slope); o1 = lrelu(o1, args.slope); }
                             pk[j] = pack_h2(o0, o1, args.h_is_fp16);
                         }
@@ -383,8 +442,11 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
+        if (e == 0 && lane == 0) GTR(5);
         if (lane == 0) bulk_wait_all();      // smem must stay valid (and the output be complete) when the caller moves on
+        if (e == 0 && lane == 0) GTR(6);
     }
+    if (MC == 2) cluster_sync_all();        // the peer may still be multicasting into this CTA's shared memory
 }
 
 template <int BN, int AB_FMT /*0 fp16, 1 bf16*/>
@@ -402,6 +464,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     gemm_run<BN, AB_FMT>(&args, args, smem, tmem_base, 2, blockIdx.x, gridDim.x);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, GemmCfg<BN>::TMEM_COLS);
+    }
+}
+
+// Cluster-pair variant (see MC above): grid must be even, launched with the static cluster shape (2, 1, 1).
+template <int BN, int AB_FMT /*0 fp16, 1 bf16*/>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 1) {
+        tmem_alloc(&tmem_slot, GemmCfg<BN>::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    gemm_run<BN, AB_FMT, 0, 2>(&args, args, smem, tmem_base, 2, blockIdx.x, gridDim.x);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

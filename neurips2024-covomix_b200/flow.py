@@ -133,6 +133,10 @@ class B200FlowSampler:
                   "covo_flow_velocity")
         return v
 
+    def last_launches(self) -> int:
+        """Kernels launched by the most recent ``sample`` call (9 on the persistent path, else launches_per_sample)."""
+        return nat.lib().covo_flow_last_launches(self._h)
+
     def launches_per_sample(self, cond_scale: float = 0.7) -> int:
         method = {"euler": nat.COVO_ODE_EULER, "midpoint": nat.COVO_ODE_MIDPOINT}[self.method]
         return nat.lib().covo_flow_launches_per_sample(self._h, method, self.n_steps(), float(cond_scale))

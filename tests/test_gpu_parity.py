@@ -398,3 +398,47 @@ def test_pipeline_batches_match_single_item_runs(dev, vosingle, vocoder):
         d = np.abs(w.astype(np.int64) - single.astype(np.int64))
         assert d.max() <= 2                      # batch composition only changes GEMM tile scheduling, not arithmetic order
     smp.close()
+
+
+# ------------------------------------------------------------------------------------------ optional execution paths
+def _fresh_sampler(dev, sd, cfg, env, **kw):
+    """A sampler created under extra environment settings (the library reads them at handle creation)."""
+    from covomix_b200.flow import B200FlowSampler
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return B200FlowSampler(sd, cfg, dev, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("method,step", [("euler", 1 / 8), ("midpoint", 0.25)])
+def test_persistent_step_kernel_matches_launch_per_op_path(dev, vosingle, method, step):
+    """COVO_FLOW_PERSISTENT=1: the whole ODE loop in one cooperative launch (csrc/flow_persistent.cuh) walks the same
+    tile loops as the launch-per-op graph, so the sampled mel must agree to fp32 round-off of the tile schedule."""
+    sd, _ = vosingle
+    ref_smp = _fresh_sampler(dev, sd, syn.VOSINGLE, {"COVO_FLOW_PERSISTENT": "0"}, torchdiffeq_ode_method=method, ode_step_size=step)
+    per_smp = _fresh_sampler(dev, sd, syn.VOSINGLE, {"COVO_FLOW_PERSISTENT": "1"}, torchdiffeq_ode_method=method, ode_step_size=step)
+    for B, N in ((1, 200), (2, 129)):
+        ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, B, N, prompt=20, seed=N)
+        a = ref_smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+        b = per_smp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+        assert per_smp.last_launches() == 9 and ref_smp.last_launches() > 100
+        assert torch.isfinite(b).all() and rel_l2(b, a) < 1e-5
+    ref_smp.close()
+    per_smp.close()
+
+
+def test_cluster_pair_gemm_path_matches(dev, vosingle):
+    """COVO_GEMM_MC=2: GEMMs as cluster pairs with a multicast weight tile (gemm_tc_pair_kernel) -- same arithmetic."""
+    sd, smp = vosingle
+    mc_smp = _fresh_sampler(dev, sd, syn.VOSINGLE, {"COVO_GEMM_MC": "2"})
+    ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, 2, 300, prompt=30, seed=8)
+    a = smp.velocity(y0.to(dev), times=0.3, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+    b = mc_smp.velocity(y0.to(dev), times=0.3, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+    assert rel_l2(b, a) < 1e-5
+    mc_smp.close()
