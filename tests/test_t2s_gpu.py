@@ -196,3 +196,56 @@ def test_sm_budget_does_not_change_results(dev, models):
     wa = B200Generator(hsd, syn.HIFIGAN_COVOMIX, dev)(mel)
     wb = B200Generator(hsd, syn.HIFIGAN_COVOMIX, dev, sm_limit=50)(mel)
     assert torch.equal(wa, wb)
+
+
+def test_full_pipeline_matches_chained_oracles(dev, models):
+    """BASELINE configs[3] end to end on a short dialogue: CoMix text-to-semantic (fp32 matrices: token-exact) -> the
+    id / cond / mask assembly of dialogue_generation.py:307-321 -> VoMix flow sampler -> HiFi-GAN, through
+    covomix_b200.pipeline, against the three CPU oracles chained on the same text, prompt, Gumbel noise and y0."""
+    from covomix_b200 import pipeline
+    from covomix_b200.flow import B200FlowSampler
+    from covomix_b200.vocoder import B200Generator
+    from oracle import covomix_oracle as forc
+    from oracle import t2s_oracle as orc
+    cfg = syn.COMIX
+    sd, ms = models["comix"]
+    t2s = ms["fp32"]
+    steps, n_prompt = 40, 24
+    text = syn.synthetic_text_ids(cfg, 1, 12, seed=21, ragged=False)
+    g = torch.Generator().manual_seed(22)
+    u = torch.rand(steps, 2, 1, cfg.n_logits, generator=g)
+    prompt_a, prompt_b = torch.randint(0, 501, (n_prompt,), generator=g), torch.randint(0, 501, (n_prompt,), generator=g)
+    prompt_mel = syn.synthetic_logmel(g, n_prompt, 160)
+
+    # ---- oracle chain
+    tgt, tmask, n_steps = orc.generate(sd, cfg, text, u, max_length=steps)
+    sem = tgt[tmask]                                                    # TextToSemanticWrapper.sample: target[target_mask]
+    half = sem.shape[0] // 2
+    item_ref = pipeline.dialogue_item(prompt_a, prompt_b, prompt_mel, sem[:half], sem[half:])
+    fcfg = syn.VOMIX
+    fsd = syn.synthetic_flow_state_dict(fcfg, 1234)
+    hsd = syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234)
+    N = item_ref["cond"].shape[0]
+    y0 = torch.randn(1, N, 80, generator=g)
+    with torch.inference_mode():
+        mel_ref = forc.flow_sample(fsd, fcfg, item_ref["phoneme_ids"][None], item_ref["cond"][None], y0, cond_scale=0.7,
+                                   method="euler", step_size=0.125)
+        gen_ref = mel_ref[0][item_ref["mask"]].transpose(0, 1).contiguous()
+        wav_ref = forc.hifigan_forward(hsd, syn.HIFIGAN_COVOMIX, gen_ref[None])
+    i16_ref = forc.wav_to_int16(wav_ref)
+
+    # ---- CUDA path through the pipeline glue
+    s1, s2, _ = pipeline.comix_pred(t2s, text[0], max_length=steps, noise=u)
+    assert torch.equal(torch.cat((s1, s2)), sem)                        # fp32 matrices reproduce the oracle's tokens
+    item = pipeline.dialogue_item(prompt_a, prompt_b, prompt_mel, s1, s2)
+    item["y0"] = y0[0]
+    smp = B200FlowSampler(fsd, fcfg, dev, torchdiffeq_ode_method="euler", ode_step_size=0.125)
+    gen = B200Generator(hsd, syn.HIFIGAN_COVOMIX, dev)
+    wav = pipeline.synthesize(smp, gen, [item], batch=1)[0]
+    assert wav.dtype == np.int16 and wav.shape == i16_ref.shape == (160 * (N - n_prompt) + 32,)
+    d = wav.astype(np.float64) - i16_ref.astype(np.float64)
+    rel = float(np.sqrt((d ** 2).mean()) / np.sqrt((i16_ref.astype(np.float64) ** 2).mean()))
+    print("PARITY", {"what": "C4 chain: T2S -> VoMix (8 Euler steps) -> HiFi-GAN, int16 waveform vs chained oracles", "rel_l2": rel})
+    assert rel < 1e-2          # measured 3.0e-3: the waveform inherits the 16-bit-operand error of the mel and of the vocoder
+    smp.close()
+    gen.close()
