@@ -14,7 +14,8 @@ def main():
     dev = torch.device("cuda:0")
     gen = B200Generator(syn.synthetic_hifigan_state_dict(syn.HIFIGAN_COVOMIX, 1234), syn.HIFIGAN_COVOMIX, dev)
     g = torch.Generator().manual_seed(5)
-    for B, T in ((1, 256), (8, 1500), (8, 4096), (1, 16384)):
+    shapes = ((8, 1500),) if len(sys.argv) > 1 and sys.argv[1] == "one" else ((1, 256), (8, 1500), (8, 4096), (1, 16384))
+    for B, T in shapes:
         mel = syn.synthetic_logmel(g, B, 80, T).to(dev)
         for _ in range(3):
             gen(mel)
