@@ -68,6 +68,7 @@ struct GemmArgs {
     int scatter;
     long long out_zs, out_rs, out_off;
     int up_s, up_p, phase_w, t_out;
+    int scatter_c_valid;             // scatter path: only channels (n % phase_w) < scatter_c_valid are stored (0: all)
     float* out_f32;
     void* out_h;
 };
@@ -415,7 +416,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                         }
                         __syncwarp();
                         const int n = ncol0 + sp * 32 + lane;
-                        if (n < args.n_valid) {
+                        if (n < args.n_valid && (args.scatter_c_valid == 0 || n % args.phase_w < args.scatter_c_valid)) {
                             const int phase = n / args.phase_w;
                             const long long base = static_cast<long long>(z) * args.out_zs + args.out_off + n;
 #pragma unroll 4

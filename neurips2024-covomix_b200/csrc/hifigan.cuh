@@ -216,6 +216,10 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
         // ---- narrow last stage: one fused kernel instead of 6 * num_kernels GEMM launches + mean + conv_post
         s.convs.clear();
         if (i + 1 == c.num_upsamples && hifi_fused_eligible(h)) {
+            // the fused kernel reads only the fp32 stream's first HF_C channels: the ConvTranspose1d need not write the
+            // 16-bit copy nor the padding channels (its scatter epilogue is per-element stores: 4x fewer of them)
+            s.up.args.out_h = nullptr;
+            s.up.args.scatter_c_valid = HF_C;
             HifiFusedArgs& f = p.fused;
             memset(&f, 0, sizeof(f));
             f.x = s.x;
