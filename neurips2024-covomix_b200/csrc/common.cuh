@@ -191,6 +191,8 @@ struct DeviceInfo {
     int device = 0;
     int num_sms = 148;
     int gemm_mc = 1;         // 2: GEMMs with >= 2 M tiles run as cluster pairs sharing the weight tile by TMA multicast
+    int gemm_cg = 0;         // 2: ... as cta_group::2 pairs (one M = 256 MMA per pair, each CTA stages half of the weight tile);
+                             // 0 (default): pairs for GEMMs of at least two waves of tiles, independent CTAs for small ones; 1: never
 };
 
 struct ASource {             // 16-bit activations [Z][rows][K], K contiguous
@@ -208,6 +210,7 @@ struct GemmOp {
     int fmt = 1;             // 0 fp16, 1 bf16
     int grid = 1;
     int mc = 1;              // 2: cluster-pair kernel (gemm_tc_pair_kernel), tmB box is (64, bn / 2)
+    int cg = 1;              // 2: cta_group::2 kernel (gemm_tc_cg2_kernel), tmB box is (64, bn / 2); excludes mc = 2
     int cat = PC_GEMM;       // profiler class
     double flops = 0.0;      // algorithmic FLOPs of this launch (real channels only; padding does not count)
 };
@@ -220,6 +223,9 @@ inline int set_gemm_attr() {
                                      GemmCfg<BN>::SMEM_BYTES));
         COVO_CK(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      GemmCfg<BN>::SMEM_BYTES));
+        if (BN >= 128)
+            COVO_CK(cudaFuncSetAttribute(gemm_tc_cg2_kernel<(BN >= 128 ? BN : 128), FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<(BN >= 128 ? BN : 128), 2>::SMEM_BYTES));
         done = true;
     }
     return COVO_OK;
@@ -258,7 +264,9 @@ inline int build_gemm(GemmOp& op, const DeviceInfo& di, const ASource& a, int q_
     if (op.bn == 0 || n_pad % op.bn) return fail(COVO_ERR_INVALID, "GEMM N_pad=%d not tileable", n_pad);
     op.fmt = is_fp16 ? 0 : 1;
     const int m_tiles_z = ceil_div(q_rows, GEMM_BM);
-    op.mc = (di.gemm_mc == 2 && m_tiles_z >= 2 && di.num_sms >= 2) ? 2 : 1;
+    const bool cg_wanted = di.gemm_cg == 2 || (di.gemm_cg == 0 && di.gemm_mc != 2 && m_tiles * (n_pad / op.bn) >= 2LL * di.num_sms);
+    op.cg = (cg_wanted && m_tiles_z >= 2 && di.num_sms >= 2 && op.bn >= 128) ? 2 : 1;
+    op.mc = (op.cg == 1 && di.gemm_mc == 2 && m_tiles_z >= 2 && di.num_sms >= 2) ? 2 : 1;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.rows), static_cast<uint64_t>(a.Z)};
         uint64_t str[2] = {static_cast<uint64_t>(a.row_stride) * 2, static_cast<uint64_t>(a.z_stride) * 2};
@@ -270,7 +278,7 @@ inline int build_gemm(GemmOp& op, const DeviceInfo& di, const ASource& a, int q_
         const int ktot = taps * a.K;
         uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(n_pad)};
         uint64_t str[1] = {static_cast<uint64_t>(ktot) * 2};
-        uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(op.bn / op.mc)};     // pair kernel: each CTA fetches half of the tile
+        uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(op.bn / (op.mc * op.cg))};     // pair kernels: each CTA fetches half of the tile
         COVO_TRY(make_tmap(&op.args.tmB, w, 2, dims, str, box, is_fp16));
     }
     op.args.rows = q_rows;
@@ -278,7 +286,7 @@ inline int build_gemm(GemmOp& op, const DeviceInfo& di, const ASource& a, int q_
     op.args.n_tiles = n_pad / op.bn;
     op.args.taps = taps;
     op.args.kc_per_tap = a.K / GEMM_BK;
-    if (op.mc == 2) {
+    if (op.mc == 2 || op.cg == 2) {
         const long long pairs = static_cast<long long>(q_Z) * ceil_div(m_tiles_z, 2) * op.args.n_tiles;
         const long long clusters = di.num_sms / 2;
         op.grid = 2 * static_cast<int>(pairs < clusters ? pairs : clusters);
@@ -333,7 +341,8 @@ inline int launch_gemm(const GemmOp& op, cudaStream_t st) {
 #define COVO_LAUNCH(BN_, F_)                                                                              \
     do {                                                                                                  \
         COVO_TRY((set_gemm_attr<BN_, F_>()));                                                             \
-        if (op.mc == 2) gemm_tc_pair_kernel<BN_, F_><<<op.grid, GEMM_THREADS, GemmCfg<BN_>::SMEM_BYTES, st>>>(op.args); \
+        if (op.cg == 2) gemm_tc_cg2_kernel<(BN_ >= 128 ? BN_ : 128), F_><<<op.grid, GEMM_THREADS, GemmCfg<(BN_ >= 128 ? BN_ : 128), 2>::SMEM_BYTES, st>>>(op.args); \
+        else if (op.mc == 2) gemm_tc_pair_kernel<BN_, F_><<<op.grid, GEMM_THREADS, GemmCfg<BN_>::SMEM_BYTES, st>>>(op.args); \
         else gemm_tc_kernel<BN_, F_><<<op.grid, GEMM_THREADS, GemmCfg<BN_>::SMEM_BYTES, st>>>(op.args);   \
     } while (0)
     if (op.fmt == 1) {

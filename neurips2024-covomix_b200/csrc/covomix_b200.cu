@@ -76,6 +76,7 @@ int covo_flow_create(const covo_flow_cfg* cfg, const void* packed_weights, size_
     // equal to independent CTAs at C3 (596.7 vs 596.0 ms) and slower at C2 (28.4 vs 27.1 ms): the L2 -> SM fabric is not
     // what binds these GEMMs, so the default stays 1.
     if (const char* v = getenv("COVO_GEMM_MC")) h->di.gemm_mc = atoi(v) == 2 ? 2 : 1;
+    if (const char* v = getenv("COVO_GEMM_CG")) h->di.gemm_cg = atoi(v);
     if (const char* v = getenv("COVO_FLOW_PERSISTENT")) h->persistent_mode = atoi(v);
     if (const char* v = getenv("COVO_FLOW_PERSISTENT_ROWS")) h->persistent_max_rows = atoi(v);
     if (const char* v = getenv("COVO_FLOW_PERSISTENT_BN")) h->persistent_bn = atoi(v);
@@ -588,6 +589,7 @@ int covo_dbg_gemm(const void* A_bf16, const void* W_bf16, const float* bias, con
     COVO_TRY(dbg_device(&di));
     if (N % 64 || K % 64) return fail(COVO_ERR_INVALID, "dbg_gemm needs N, K multiples of 64");
     if (const char* v = getenv("COVO_GEMM_MC")) di.gemm_mc = atoi(v) == 2 ? 2 : 1;
+    if (const char* v = getenv("COVO_GEMM_CG")) di.gemm_cg = atoi(v);
     GemmOp op;
     gemm_defaults(op.args);
     COVO_TRY(build_gemm(op, di, a2d(A_bf16, K, M), M, 1, W_bf16, N, 1, 0, force_bn));

@@ -656,10 +656,11 @@ inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, fl
         return fail(COVO_ERR_INVALID, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     }
     p->persistent = flow_persistent_eligible(h, *p);
-    const int saved_mc = h->di.gemm_mc;
-    if (p->persistent) h->di.gemm_mc = 1;          // the cooperative kernel is not launched in clusters
+    const int saved_mc = h->di.gemm_mc, saved_cg = h->di.gemm_cg;
+    if (p->persistent) h->di.gemm_mc = h->di.gemm_cg = 1;          // the cooperative kernel is not launched in clusters
     int rc = flow_build_ops(h, *p);
     h->di.gemm_mc = saved_mc;
+    h->di.gemm_cg = saved_cg;
     if (rc != COVO_OK) {
         delete p;
         return rc;

@@ -34,7 +34,6 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_MAX_TAPS = 16;
 constexpr int GEMM_STAGE_A_BYTES = GEMM_BM * GEMM_BK * 2;
 constexpr int GEMM_EPI_BUF_BYTES = 4096;    // per epilogue warp: [32 rows x 128 B], 128B-swizzled
-constexpr int GEMM_EPI_STAGING_BYTES = GEMM_EPI_WARPS * GEMM_EPI_BUF_BYTES;
 
 enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2 };
 
@@ -80,13 +79,21 @@ __device__ long long* g_gemm_trace = nullptr;
 __device__ int g_gemm_trace_n = 0;
 #define GTR(slot) do { if (g_gemm_trace != nullptr && blockIdx.x == 0 && gtr_base >= 0) g_gemm_trace[gtr_base + (slot)] = clock64(); } while (0)
 
-template <int BN>
+// CG = 2: the CTA is half of a cta_group::2 pair (M = 256 per MMA): it stages its own 128 rows of A and HALF of the weight
+// tile per K chunk (32 KB instead of 48 KB at BN = 256), so the ring is deeper and shared-memory / L2 operand traffic per
+// FLOP drops by a third.
+template <int BN, int CG = 1>
 struct GemmCfg {
-    static constexpr int STAGE_B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_B_BYTES = BN / CG * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    // Two staging buffers per epilogue warp wherever a stage can be spared for them (everything but the 48 KB stages of the
+    // single-CTA BN = 256 tile): the fp32 residual sub-tile of step k+1 is in flight while step k is added and stored.
+    static constexpr int EPI_BUFS = (CG == 2 || BN < 256) ? 2 : 1;
+    static constexpr int STAGES = CG == 2 ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 4 : (BN == 128 ? 5 : 6));
+    static constexpr int EPI_STAGING_BYTES = GEMM_EPI_WARPS * EPI_BUFS * GEMM_EPI_BUF_BYTES;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_STAGING_BYTES + 512 /*barriers*/ + 1024 /*align*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 512 /*barriers*/ + 1024 /*align*/;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b, int is_fp16) {
@@ -113,18 +120,24 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b, int is_fp16) {
 //     (the K loop of a 128 x 256 tile asks the fabric for 96 B/clk/SM; chip-wide that is more than L2 delivers).
 //     tmB's box is then (64, BN/2).  A stage may only be refilled when BOTH CTAs' MMAs have read it: every MMA commit on
 //     empty[] is multicast to the pair (count 2).
-template <int BN, int AB_FMT /*0 fp16, 1 bf16*/, int ROLE = 0, int MC = 1>
+// CG: 2 = cta_group::2 pair (launch with cluster dims (2,1,1), TMEM allocated with tmem_alloc_cg2 by both CTAs): same pair-tile
+//     schedule as MC = 2, but ONE MMA of M = 256 per K16 step issued by the even-rank CTA; each CTA keeps only its own half
+//     of the weight tile; tmB's box is (64, BN/2).  Requires MC = 1.
+template <int BN, int AB_FMT /*0 fp16, 1 bf16*/, int ROLE = 0, int MC_ = 1, int CG = 1>
 __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& args, uint8_t* smem, uint32_t tmem_base,
                                          int epi_warp0, int cta, int n_ctas) {
-    using Cfg = GemmCfg<BN>;
+    static_assert(CG == 1 || MC_ == 1, "cta_group::2 and the multicast pair are alternatives");
+    constexpr int MC = CG == 2 ? 2 : MC_;              // pair-tile schedule in both cases
+    constexpr bool MCAST = MC_ == 2;                   // weight halves exchanged by TMA multicast (cta_group::1 MMAs)
+    using Cfg = GemmCfg<BN, CG>;
     uint8_t* stage_base = smem;
     uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_STAGING_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::EPI_STAGING_BYTES);
     uint64_t* full = bars;                         // [STAGES]
     uint64_t* empty = bars + Cfg::STAGES;          // [STAGES]
     uint64_t* tfull = bars + 2 * Cfg::STAGES;      // [2]
     uint64_t* tempty = bars + 2 * Cfg::STAGES + 2; // [2]
-    uint64_t* rbar = bars + 2 * Cfg::STAGES + 4;   // [GEMM_EPI_WARPS] residual sub-tile landed
+    uint64_t* rbar = bars + 2 * Cfg::STAGES + 4;   // [GEMM_EPI_WARPS * EPI_BUFS] residual sub-tile landed
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -157,13 +170,13 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
         tma_prefetch_desc(&desc->tmB);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], MC);
+            mbar_init(&empty[s], MCAST ? 2 : 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], EPI_WARPS_ACTIVE);
+            mbar_init(&tempty[a], EPI_WARPS_ACTIVE * CG);      // CG = 2: the leader's barrier collects both CTAs' epilogue warps
         }
-        for (int w = 0; w < GEMM_EPI_WARPS; ++w) mbar_init(&rbar[w], 1);
+        for (int w = 0; w < GEMM_EPI_WARPS * Cfg::EPI_BUFS; ++w) mbar_init(&rbar[w], 1);
         fence_mbar_init();
     }
     if (MC == 2) cluster_sync_all();        // the peer's multicast may signal this CTA's barriers from now on
@@ -190,9 +203,18 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                         mbar_wait(&empty[s], ph ^ 1);
                         uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
                         uint8_t* sb = sa + GEMM_STAGE_A_BYTES;
+                        if (CG == 2) {
+                            // both CTAs' bytes are counted on the LEADER's barrier (its MMA thread is the only consumer)
+                            if (crank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+                            const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0);
+                            tma_load_3d_cg2(sa, &desc->tmA, lbar, kc * GEMM_BK, arow, az);
+                            tma_load_2d_cg2(sb, &desc->tmB, lbar, (tap * args.kc_per_tap + kc) * GEMM_BK, n0 + crank * (BN / 2));
+                            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                            continue;
+                        }
                         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
                         tma_load_3d(sa, &desc->tmA, &full[s], kc * GEMM_BK, arow, az);
-                        if (MC == 2)        // this CTA's half of the weight tile, into both CTAs of the pair
+                        if (MCAST)          // this CTA's half of the weight tile, into both CTAs of the pair
                             tma_load_2d_mc(sb + crank * (Cfg::STAGE_B_BYTES / 2), &desc->tmB, &full[s],
                                            (tap * args.kc_per_tap + kc) * GEMM_BK, n0 + crank * (BN / 2), 0x3);
                         else
@@ -204,8 +226,8 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
         }
     } else if (ROLE != 2 && warp == 1) {
         // ===================================================== MMA issuer (elect.sync: ptxas keeps operands in uniform registers)
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, AB_FMT, 0, 0);
+        if ((CG == 1 || crank == 0) && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM * CG, BN, AB_FMT, 0, 0);
             // descriptors of stage 0, built once; per stage / per K16 step only the start-address field is advanced
             const uint64_t dA0 = smem_desc_sw128(smem_u32(stage_base), 1024, 16);
             const uint64_t dB0 = smem_desc_sw128(smem_u32(stage_base) + GEMM_STAGE_A_BYTES, 1024, 16);
@@ -224,13 +246,17 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                     const uint64_t da = desc_advance(dA0, s * Cfg::STAGE_BYTES);
                     const uint64_t db = desc_advance(dB0, s * Cfg::STAGE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_f16(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (it | k) != 0);
-                    if (MC == 2) umma_commit_mc(&empty[s], 0x3);
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        if (CG == 2) umma_f16_cg2(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (it | k) != 0);
+                        else umma_f16(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (it | k) != 0);
+                    }
+                    if (CG == 2) umma_commit_cg2_mc(&empty[s], 0x3);
+                    else if (MCAST) umma_commit_mc(&empty[s], 0x3);
                     else umma_commit(&empty[s]);
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[as]);
+                if (CG == 2) umma_commit_cg2_mc(&tfull[as], 0x3);
+                else umma_commit(&tfull[as]);
                 GTR(3);
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
@@ -241,12 +267,16 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
         const int e = warp - epi_warp0;
         const int lq = warp & 3;
         const int chalf = e >> 2;
-        uint8_t* buf = staging + e * GEMM_EPI_BUF_BYTES;          // [32 rows][128 B]; 16-B chunk c of row r at (c ^ (r&7))*16
+        constexpr int NB = Cfg::EPI_BUFS;
+        uint8_t* buf = staging + e * NB * GEMM_EPI_BUF_BYTES;     // NB x [32 rows][128 B]; 16-B chunk c of row r at (c ^ (r&7))*16
         uint8_t* my_row = buf + lane * 128;
         const uint32_t my_row_s = smem_u32(my_row);
         const int sw = lane & 7;
-        uint64_t* my_rbar = &rbar[e];
-        uint32_t rph = 0;
+        uint64_t* my_rbar = &rbar[e * NB];
+        uint32_t rph = 0;                                         // NB = 2: bit j = parity of my_rbar[j]
+        // NB = 2: fp32 sub-tile step k of this warp uses buffer k & 1; `pre`: the residual of step kstep has been requested
+        uint32_t kstep = 0, kh = 0;
+        bool pre = false;
         int as = 0;
         uint32_t aph = 0;
         constexpr int COLS_PER_WARP = (BN >= 128) ? BN / 2 : BN;
@@ -263,10 +293,20 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
             const bool rows_live = q_warp0 < args.rows;            // warp-uniform: does this warp own any valid row?
 
             // residual sub-tile of the first fp32 sub-pass: fetched while the MMAs of this tile still run
-            if (has_res && rows_live && n0 < args.n_valid && lane == 0) {
-                bulk_wait_read0();
-                mbar_expect_tx(my_rbar, GEMM_EPI_BUF_BYTES);
-                tma_load_3d(buf, &desc->tmRes, my_rbar, n0, q_warp0, z);
+            if (NB == 1) {
+                if (has_res && rows_live && n0 < args.n_valid && lane == 0) {
+                    bulk_wait_read0();
+                    mbar_expect_tx(my_rbar, GEMM_EPI_BUF_BYTES);
+                    tma_load_3d(buf, &desc->tmRes, my_rbar, n0, q_warp0, z);
+                }
+            } else if (has_res && use_tma && !pre && rows_live && n0 < args.n_valid) {
+                if (lane == 0) {
+                    const int j = kstep & 1;
+                    bulk_wait_read0();
+                    mbar_expect_tx(&my_rbar[j], GEMM_EPI_BUF_BYTES);
+                    tma_load_3d(buf + j * GEMM_EPI_BUF_BYTES, &desc->tmRes, &my_rbar[j], n0, q_warp0, z);
+                }
+                pre = true;
             }
 
             // RoPE factors of this thread's row: the same 32 (cos, sin) pairs serve every head of the tile, and the row is known
@@ -300,7 +340,10 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                     // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[as]);
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+                        else mbar_arrive(&tempty[as]);
+                    }
                 }
                 const int ncol0 = n0 + c * 64;
                 if (!rows_live || ncol0 >= args.n_valid) continue;
@@ -330,7 +373,107 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                         r[4 * j + 3] = __float_as_uint(s3);
                     }
                 }
-                if (use_tma) {
+                if (use_tma && NB == 2) {
+                    // ---------------- two staging buffers per warp.  fp32 sub-tile step k: buffer k & 1; at its start the residual
+                    // of step k+1 (same chunk, next chunk or this warp's next tile) is requested into the other buffer, so a
+                    // residual load is in flight while the previous sub-tile is added, written back and stored.
+                    if (args.has_out_f32) {
+#pragma unroll
+                        for (int sp = 0; sp < 2; ++sp) {
+                            const int ncol = ncol0 + sp * 32;
+                            if (ncol < args.n_valid) {
+                                const int j = kstep & 1;
+                                uint8_t* bj = buf + j * GEMM_EPI_BUF_BYTES;
+                                const uint32_t row_s = my_row_s + j * GEMM_EPI_BUF_BYTES;
+                                if (has_res) {
+                                    int nq = q_warp0, nz = z, nn = -1;                 // the next fp32 sub-tile of this warp
+                                    if (sp == 0 && ncol + 32 < args.n_valid) nn = ncol + 32;
+                                    else if (c + 1 < NCH && ncol0 + 64 < args.n_valid) nn = ncol0 + 64;
+                                    else if (tile + n_ctas < total_tiles) {
+                                        const int t2 = tile + n_ctas;
+                                        const int mz2 = t2 / args.n_tiles;
+                                        nq = ((mz2 % m_tiles_per_z) * MC + crank) * GEMM_BM + lq * 32;
+                                        nz = mz2 / m_tiles_per_z;
+                                        const int n2 = (t2 % args.n_tiles) * BN + chalf * COLS_PER_WARP;
+                                        if (nq < args.rows && n2 < args.n_valid) nn = n2;
+                                    }
+                                    if (lane == 0) {
+                                        bulk_wait_read0();                              // both buffers' stores have drained
+                                        if (!pre) {
+                                            mbar_expect_tx(&my_rbar[j], GEMM_EPI_BUF_BYTES);
+                                            tma_load_3d(bj, &desc->tmRes, &my_rbar[j], ncol, q_warp0, z);
+                                        }
+                                        if (nn >= 0) {
+                                            mbar_expect_tx(&my_rbar[j ^ 1], GEMM_EPI_BUF_BYTES);
+                                            tma_load_3d(buf + (j ^ 1) * GEMM_EPI_BUF_BYTES, &desc->tmRes, &my_rbar[j ^ 1], nn, nq, nz);
+                                        }
+                                    }
+                                    pre = nn >= 0;
+                                    mbar_wait(&my_rbar[j], (rph >> j) & 1u);
+                                    rph ^= 1u << j;
+#pragma unroll
+                                    for (int c4 = 0; c4 < 8; ++c4) {
+                                        const float4 v = lds128f(row_s + ((c4 ^ sw) << 4));
+                                        const int b = sp * 32 + 4 * c4;
+                                        float s0, s1, s2, s3;
+                                        add2(s0, s1, __uint_as_float(r[b]), __uint_as_float(r[b + 1]), v.x, v.y);
+                                        add2(s2, s3, __uint_as_float(r[b + 2]), __uint_as_float(r[b + 3]), v.z, v.w);
+                                        r[b] = __float_as_uint(s0);
+                                        r[b + 1] = __float_as_uint(s1);
+                                        r[b + 2] = __float_as_uint(s2);
+                                        r[b + 3] = __float_as_uint(s3);
+                                    }
+                                } else if (lane == 0) {
+                                    bulk_wait_read1();          // the store that read this buffer (two stores ago) has drained
+                                }
+                                __syncwarp();
+#pragma unroll
+                                for (int c4 = 0; c4 < 8; ++c4) {
+                                    const int b = sp * 32 + 4 * c4;
+                                    sts128(row_s + ((c4 ^ sw) << 4), r[b], r[b + 1], r[b + 2], r[b + 3]);
+                                }
+                                fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_3d(&desc->tmOutF, bj, ncol, q_warp0, z);
+                                    bulk_commit();
+                                }
+                                ++kstep;
+                            }
+                        }
+                    }
+                    if (args.has_out_h) {
+                        // 16-bit [32 x 64] sub-tile: through the buffer the last fp32 step used (the other one may hold a
+                        // prefetched residual); without fp32 steps the two buffers simply alternate
+                        uint32_t pk[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float o0 = __uint_as_float(r[2 * j]), o1 = __uint_as_float(r[2 * j + 1]);
+                            if (args.act_h == ACT_GELU) gelu_fast2(o0, o1, o0, o1);
+                            else if (args.act_h == ACT_LRELU) { o0 = lrelu(o0, args.slope); o1 = lrelu(o1, args.slope); }
+                            pk[j] = pack_h2(o0, o1, args.h_is_fp16);
+                        }
+                        int j;
+                        if (args.has_out_f32) {
+                            j = (kstep - 1) & 1;
+                            if (lane == 0) bulk_wait_read0();
+                        } else {
+                            j = kh++ & 1;
+                            if (lane == 0) bulk_wait_read1();
+                        }
+                        const uint32_t row_s = my_row_s + j * GEMM_EPI_BUF_BYTES;
+                        __syncwarp();
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4)
+                            sts128(row_s + ((c4 ^ sw) << 4), pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&desc->tmOutH, buf + j * GEMM_EPI_BUF_BYTES, ncol0, q_warp0, z);
+                            bulk_commit();
+                        }
+                    }
+                } else if (use_tma) {
                     // ---------------- fp32 output (+ residual): two [32 x 32] fp32 sub-tiles
                     if (args.has_out_f32) {
 #pragma unroll
@@ -494,6 +637,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, GemmCfg<BN>::TMEM_COLS);
+    }
+}
+
+// cta_group::2 variant (see CG above): grid must be even, static cluster shape (2, 1, 1); TMEM is allocated for the pair.
+template <int BN, int AB_FMT /*0 fp16, 1 bf16*/>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_tc_cg2_kernel(const __grid_constant__ GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 1) {
+        tmem_alloc_cg2(&tmem_slot, GemmCfg<BN, 2>::TMEM_COLS);
+        tmem_relinquish_cg2();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    gemm_run<BN, AB_FMT, 0, 1, 2>(&args, args, smem, tmem_base, 2, blockIdx.x, gridDim.x);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, GemmCfg<BN, 2>::TMEM_COLS);
     }
 }
 

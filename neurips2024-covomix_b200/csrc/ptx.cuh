@@ -118,6 +118,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING their smem source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one (two staging buffers used alternately: the buffer of two stores ago is free)
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
@@ -167,6 +169,53 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // Same, arriving on the mbarrier at this offset in every CTA of the cluster named in cta_mask.
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+// ----------------------------------------------------------------------------- cta_group::2 (CTA pair = one MMA unit)
+// The two CTAs of a (2,1,1) cluster issue ONE tcgen05.mma of M = 256: each CTA supplies its 128 rows of A and its half of
+// the N rows of B from its own shared memory (same offsets in both CTAs) and receives its 128 rows of D in its own TMEM.
+// Only the even-rank CTA (the leader) issues MMAs and commits; TMA loads of both CTAs signal the LEADER's mbarrier.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta_rank) {       // shared::cta address -> shared::cluster address of that CTA
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {            // arrive on an mbarrier of any CTA of the cluster
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {    // the same warp of BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all MMAs issued so far by this thread have completed) on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"(cta_mask)
                  : "memory");
 }
@@ -264,27 +313,25 @@ __device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, f
         "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
         : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
-// gelu_fast for a pair, on packed fp32 instructions: 0.5 x (1 + erf(x / sqrt 2)) = 0.5 x + |0.5 x| erf(|x| / sqrt 2)
-// (same A&S 7.1.26 polynomial; ~10 instructions per element instead of ~22, 2 MUFU each)
+// GELU for a pair on packed fp32 instructions with ONE MUFU per element:
+//   erf(z) = 1 - 2^(-z q(z)) for z >= 0, q a degree-4 minimax fit of -log2(erfc(z)) / z (|erf error| <= 7e-7; q is positive and
+//   increasing for every z >= 0, so large |x| saturates cleanly), and with h = x / 2, z = |h| sqrt 2:
+//   GELU(x) = h (1 + erf(x / sqrt 2)) = max(x, 0) - |h| 2^(-z q(z))            (|error| <= 1.2e-6 for |x| <= 40)
+// 8 packed FMA-pipe instructions + 2 EX2 per pair (the A&S 7.1.26 form needed 11 + 2 RCP + 2 EX2: the epilogue of a K = 1024
+// GEMM tile was bound by the MUFU, 4096 of the main loop's 8192 cycles).  Only used where the result is rounded to 16 bits.
 __device__ __forceinline__ void gelu_fast2(float& y0, float& y1, float x0, float x1) {
-    const float a0 = fabsf(x0), a1 = fabsf(x1);
-    float z0, z1, t0, t1, p0, p1, e0, e1, h0, h1;
-    mul2(z0, z1, a0, a1, 0.70710678118654752440f, 0.70710678118654752440f);
-    fma2(t0, t1, z0, z1, 0.3275911f, 0.3275911f, 1.0f, 1.0f);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(t0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(t1));
-    fma2(p0, p1, t0, t1, 1.061405429f, 1.061405429f, -1.453152027f, -1.453152027f);
-    fma2(p0, p1, p0, p1, t0, t1, 1.421413741f, 1.421413741f);
-    fma2(p0, p1, p0, p1, t0, t1, -0.284496736f, -0.284496736f);
-    fma2(p0, p1, p0, p1, t0, t1, 0.254829592f, 0.254829592f);
-    mul2(p0, p1, p0, p1, t0, t1);
-    mul2(e0, e1, z0, z1, z0, z1);
-    mul2(e0, e1, e0, e1, -1.4426950408889634f, -1.4426950408889634f);
+    float h0, h1, z0, z1, q0, q1, e0, e1;
+    mul2(h0, h1, x0, x1, 0.5f, 0.5f);
+    const float n0 = __uint_as_float(__float_as_uint(h0) | 0x80000000u), n1 = __uint_as_float(__float_as_uint(h1) | 0x80000000u);   // -|h|
+    mul2(z0, z1, n0, n1, -1.41421356237309505f, -1.41421356237309505f);
+    fma2(q0, q1, z0, z1, -0.002944216364994645f, -0.002944216364994645f, 0.029590299353003502f, 0.029590299353003502f);
+    fma2(q0, q1, q0, q1, z0, z1, -0.14866594970226288f, -0.14866594970226288f);
+    fma2(q0, q1, q0, q1, z0, z1, -0.9185092449188232f, -0.9185092449188232f);
+    fma2(q0, q1, q0, q1, z0, z1, -1.6278890371322632f, -1.6278890371322632f);       // -q(z)
+    mul2(e0, e1, z0, z1, q0, q1);
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(e0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(e1));
-    fma2(e0, e1, p0, p1, -e0, -e1, 1.0f, 1.0f);            // erf(|x| / sqrt 2)
-    mul2(h0, h1, x0, x1, 0.5f, 0.5f);
-    fma2(y0, y1, fabsf(h0), fabsf(h1), e0, e1, h0, h1);
+    fma2(y0, y1, n0, n1, e0, e1, fmaxf(x0, 0.f), fmaxf(x1, 0.f));
 }
 __device__ __forceinline__ float lrelu(float x, float s) { return x > 0.f ? x : x * s; }
 

@@ -442,3 +442,19 @@ def test_cluster_pair_gemm_path_matches(dev, vosingle):
     b = mc_smp.velocity(y0.to(dev), times=0.3, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
     assert rel_l2(b, a) < 1e-5
     mc_smp.close()
+
+
+def test_cta_pair_mma_gemm_path_matches(dev, vosingle):
+    """COVO_GEMM_CG=2 forces every GEMM with >= 2 M tiles onto the cta_group::2 kernel (gemm_tc_cg2_kernel: one M = 256 MMA per
+    CTA pair, each CTA staging half of the weight tile; the default uses it only for multi-wave GEMMs), COVO_GEMM_CG=1 forbids
+    it.  Same products, same K order -> same results.  N = 330 gives 11 M tiles: the last pair has a phantom second tile."""
+    sd, _ = vosingle
+    one = _fresh_sampler(dev, sd, syn.VOSINGLE, {"COVO_GEMM_CG": "1"})
+    two = _fresh_sampler(dev, sd, syn.VOSINGLE, {"COVO_GEMM_CG": "2"})
+    for B, N in ((2, 330), (1, 129)):
+        ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOSINGLE, B, N, prompt=30, seed=9)
+        a = one.velocity(y0.to(dev), times=0.3, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+        b = two.velocity(y0.to(dev), times=0.3, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+        assert torch.isfinite(b).all() and rel_l2(b, a) < 1e-5
+    one.close()
+    two.close()
