@@ -88,8 +88,10 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
     // Two staging buffers per epilogue warp wherever a stage can be spared for them (everything but the 48 KB stages of the
     // single-CTA BN = 256 tile): the fp32 residual sub-tile of step k+1 is in flight while step k is added and stored.
-    static constexpr int EPI_BUFS = (CG == 2 || BN < 256) ? 2 : 1;
-    static constexpr int STAGES = CG == 2 ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 4 : (BN == 128 ? 5 : 6));
+    // (Measured: `out` 67.0 -> 63.7 us with 5 stages + 2 buffers on the cta_group::2 BN = 256 tile, but every other layer GEMM
+    // loses 2-4 % to the shallower ring, so that tile keeps 6 stages and one buffer; the vocoder's narrow tiles gain 2 %.)
+    static constexpr int EPI_BUFS = BN < 256 ? 2 : 1;
+    static constexpr int STAGES = CG == 2 ? (BN == 256 ? 6 : 6) : ((BN == 256) ? 4 : (BN == 128 ? 5 : 6));
     static constexpr int EPI_STAGING_BYTES = GEMM_EPI_WARPS * EPI_BUFS * GEMM_EPI_BUF_BYTES;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 512 /*barriers*/ + 1024 /*align*/;
