@@ -121,7 +121,7 @@ int covo_flow_launches_per_sample(const covo_flow* h, int method, int n_steps, f
     const int half = h->cfg.depth / 2;
     const int per_net = 2 + 7 * h->cfg.depth + half + 2;
     const int nfe = flow_num_times(method, n_steps);
-    return 7 + 1 + nfe * (per_net + 1);
+    return 2 + 1 + nfe * (per_net + 1);      // per-call prologue (embedding gather, e_const), state -> input, the evaluations
 }
 
 int covo_flow_last_launches(const covo_flow* h) { return h ? h->last_launches : 0; }

@@ -38,6 +38,9 @@ struct FlowPlan {
     __nv_bfloat16 *a_pc = nullptr, *xin = nullptr, *slots = nullptr, *a_norm = nullptr, *qkv = nullptr, *attn_o = nullptr,
                   *ffh = nullptr;
     float *e_const = nullptr, *h0 = nullptr, *x = nullptr, *vpred = nullptr;
+    // Tables that depend on the evaluation times and the weights only (time MLP, AdaLN gamma/beta, RoPE): plan-owned device memory, filled once when the plan is built (per call for covo_flow_velocity,
+    // whose t is an argument) -- never in the caller's workspace, which may be recycled between calls.
+    void* tables = nullptr;
     // ops
     GemmOp op_const, op_embed, op_pred;
     std::vector<GemmOp> op_skip, op_qkv, op_out, op_ff1, op_ff2;
@@ -133,11 +136,6 @@ inline size_t flow_layout(const covo_flow* h, FlowPlan& p) {
     p.x_state = a.take<float>(static_cast<size_t>(BN) * c.dim_x);
     p.x_in = a.take<float>(static_cast<size_t>(BN) * c.dim_x);
     p.v_out = a.take<float>(static_cast<size_t>(BN) * c.dim_x);
-    p.d_times = a.take<float>(FLOW_MAX_TIMES);
-    p.tfeat = a.take<float>(static_cast<size_t>(p.n_t) * D);
-    p.temb = a.take<float>(static_cast<size_t>(p.n_t) * D * 4);
-    p.gb = a.take<float>(static_cast<size_t>(p.n_t) * c.depth * 4 * D);
-    p.rope = a.take<float2>(static_cast<size_t>(p.N) * 32);
     p.a_pc = a.take<__nv_bfloat16>(static_cast<size_t>(M) * h->kpc);
     p.xin = a.take<__nv_bfloat16>(static_cast<size_t>(M) * h->ldx);
     p.slots = a.take<__nv_bfloat16>(static_cast<size_t>(c.depth / 2 + 1) * M * D);
@@ -149,6 +147,19 @@ inline size_t flow_layout(const covo_flow* h, FlowPlan& p) {
     p.h0 = a.take<float>(static_cast<size_t>(M) * D);
     p.x = a.take<float>(static_cast<size_t>(M) * D);
     p.vpred = a.take<float>(static_cast<size_t>(M) * c.dim_x);
+    return align_up(a.off, 256);
+}
+
+// Plan-owned tables (see FlowPlan::tables).  base == null: size query.
+inline size_t flow_layout_tables(const covo_flow* h, FlowPlan& p, void* base) {
+    const covo_flow_cfg& c = h->cfg;
+    const int D = c.dim;
+    Arena a(base, static_cast<size_t>(-1));
+    p.d_times = a.take<float>(FLOW_MAX_TIMES);
+    p.tfeat = a.take<float>(static_cast<size_t>(p.n_t) * D);
+    p.temb = a.take<float>(static_cast<size_t>(p.n_t) * D * 4);
+    p.gb = a.take<float>(static_cast<size_t>(p.n_t) * c.depth * 4 * D);
+    p.rope = a.take<float2>(static_cast<size_t>(p.N) * 32);
     return align_up(a.off, 256);
 }
 
@@ -264,6 +275,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
             }
             COVO_TRY(gemm_set_outputs(op, p.x, p.x, next_h, D, M, 1, D, 0, 0));
             op.args.bias = lw.ff2_b.as<float>();
+
             op.flops = 2.0 * M * D * c.ff_mult * D;
         }
     }
@@ -309,32 +321,46 @@ inline int launch_rmsnorm(const float* x, const float* g, const float* b, __nv_b
     return COVO_OK;
 }
 
-// Work that depends on the call's inputs but not on the ODE state: time tables, RoPE table, e_const.
-inline int flow_enqueue_prologue(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
+// Tables that depend on the evaluation times only: time MLP (acoustic.py:361-365), the 4 x depth AdaLN projections of every
+// time (:198-204), RoPE factors (:126-130).  Once per plan (per call for single_eval).
+inline int flow_enqueue_tables(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
     const covo_flow_cfg& c = h->cfg;
     const int D = c.dim;
     TimesArg ta;
-    ProfScope* ps = new ProfScope(PC_PROLOGUE, 0.0, st);
+    ProfScope ps(PC_PROLOGUE, 0.0, st);
     memcpy(ta.t, p.times, sizeof(float) * p.n_t);
     set_times_kernel<<<1, FLOW_MAX_TIMES, 0, st>>>(p.d_times, ta, p.n_t);
     time_features_kernel<<<p.n_t, 256, 0, st>>>(p.d_times, h->time_w.as<float>(), p.tfeat, p.n_t, D / 2);
     {
         dim3 g(ceil_div(4 * D, 64), ceil_div(p.n_t, 64));
-        sgemm_nt_kernel<<<g, 256, 0, st>>>(p.tfeat, h->time_lin_w.as<float>(), h->time_lin_b.as<float>(), p.temb, p.n_t, 4 * D,
-                                           D, SG_SILU);
+        sgemm_nt_kernel<float><<<g, 256, 0, st>>>(p.tfeat, D, h->time_lin_w.as<float>(), h->time_lin_b.as<float>(), p.temb, 4 * D,
+                                                  p.n_t, 4 * D, D, SG_SILU);
     }
+    const int NO = c.depth * 4 * D;           // per layer: gamma1 | beta1 | gamma2 | beta2
     {
-        const int NO = c.depth * 4 * D;       // per layer: gamma1 | beta1 | gamma2 | beta2
         dim3 g(ceil_div(NO, 64), ceil_div(p.n_t, 64));
-        sgemm_nt_kernel<<<g, 256, 0, st>>>(p.temb, h->gb_w.as<float>(), h->gb_b.as<float>(), p.gb, p.n_t, NO, 4 * D, SG_NONE);
+        sgemm_nt_kernel<float><<<g, 256, 0, st>>>(p.temb, 4 * D, h->gb_w.as<float>(), h->gb_b.as<float>(), p.gb, NO, p.n_t, NO, 4 * D,
+                                                  SG_NONE);
     }
+    *launches += 4;
     rope_table_kernel<<<ceil_div(p.N * 32, 256), 256, 0, st>>>(h->inv_freq.as<float>(), p.rope, p.N, 32);
-    embed_input_kernel<<<p.M, 256, 0, st>>>(p.ids, p.cond, h->emb_table.as<float>(), h->null_cond.as<float>(), p.a_pc, p.BN,
-                                            c.n_streams, c.dim_phoneme_emb, c.dim_in, c.num_phoneme_tokens, h->kpc);
-    delete ps;
+    ++*launches;
+    COVO_CK(cudaGetLastError());
+    return COVO_OK;
+}
+
+// Work that depends on the call's inputs but not on the ODE state: e_const = [emb | cond] W_pc^T + b.
+inline int flow_enqueue_prologue(covo_flow* h, FlowPlan& p, cudaStream_t st, int* launches) {
+    const covo_flow_cfg& c = h->cfg;
+    if (p.single_eval) COVO_TRY(flow_enqueue_tables(h, p, st, launches));
+    {
+        ProfScope ps(PC_PROLOGUE, 0.0, st);
+        embed_input_kernel<<<p.M, 256, 0, st>>>(p.ids, p.cond, h->emb_table.as<float>(), h->null_cond.as<float>(), p.a_pc, p.BN,
+                                                c.n_streams, c.dim_phoneme_emb, c.dim_in, c.num_phoneme_tokens, h->kpc);
+    }
     COVO_CK(cudaGetLastError());
     COVO_TRY(launch_gemm(p.op_const, st));
-    *launches += 7;
+    *launches += 2;
     return COVO_OK;
 }
 
@@ -454,6 +480,7 @@ inline void flow_free_plan(FlowPlan* p) {
     if (p->d_ops) cudaFree(p->d_ops);
     if (p->d_evals) cudaFree(p->d_evals);
     if (p->d_sync) cudaFree(p->d_sync);
+    if (p->tables) cudaFree(p->tables);
     delete p;
 }
 
@@ -656,13 +683,26 @@ inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, fl
         return fail(COVO_ERR_INVALID, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     }
     p->persistent = flow_persistent_eligible(h, *p);
+    {
+        const size_t tb = flow_layout_tables(h, *p, nullptr);
+        if (cudaMalloc(&p->tables, tb) != cudaSuccess) {
+            delete p;
+            return fail(COVO_ERR_CUDA, "cudaMalloc of %zu bytes (time tables) failed", tb);
+        }
+        flow_layout_tables(h, *p, p->tables);
+    }
     const int saved_mc = h->di.gemm_mc, saved_cg = h->di.gemm_cg;
     if (p->persistent) h->di.gemm_mc = h->di.gemm_cg = 1;          // the cooperative kernel is not launched in clusters
     int rc = flow_build_ops(h, *p);
     h->di.gemm_mc = saved_mc;
     h->di.gemm_cg = saved_cg;
+    if (rc == COVO_OK && !single_eval) {
+        int tl = 0;
+        rc = flow_enqueue_tables(h, *p, h->capture_stream, &tl);
+        if (rc == COVO_OK && cudaStreamSynchronize(h->capture_stream) != cudaSuccess) rc = fail(COVO_ERR_CUDA, "time tables failed");
+    }
     if (rc != COVO_OK) {
-        delete p;
+        flow_free_plan(p);
         return rc;
     }
     // padding columns of the bf16 operands (a_pc, xin) must be exact zeros (they meet zero weight columns, but
@@ -683,13 +723,13 @@ inline int flow_get_plan(covo_flow* h, int B, int N, int method, int n_steps, fl
         cudaError_t e = cudaStreamEndCapture(h->capture_stream, &graph);
         if (rc != COVO_OK || e != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);
-            delete p;
+            flow_free_plan(p);
             return rc != COVO_OK ? rc : fail(COVO_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
         }
         e = cudaGraphInstantiate(&p->exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) {
-            delete p;
+            flow_free_plan(p);
             return fail(COVO_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
         }
         p->launches = launches;

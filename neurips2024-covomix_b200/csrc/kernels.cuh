@@ -13,9 +13,14 @@ namespace covo {
 // ------------------------------------------------------------------------------------------------
 enum : int { SG_NONE = 0, SG_SILU = 1 };
 
-__global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                       const float* __restrict__ bias, float* __restrict__ C, int M,
-                                                       int N, int K, int act) {
+__device__ __forceinline__ float sg_ldw(const float* p) { return *p; }
+__device__ __forceinline__ float sg_ldw(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// C[m, n] = act(sum_k A[m*lda + k] * B[n*K + k] + bias[n]),  C row pitch ldc.  B: fp32 or bf16 (the packed Linear weights).
+template <class TB>
+__global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, long long lda, const TB* __restrict__ B,
+                                                       const float* __restrict__ bias, float* __restrict__ C, long long ldc,
+                                                       int M, int N, int K, int act) {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -24,8 +29,8 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__
     for (int k0 = 0; k0 < K; k0 += 16) {
         for (int i = threadIdx.x; i < 64 * 16; i += 256) {
             const int r = i >> 4, kk = i & 15;
-            As[kk][r] = (m0 + r < M && k0 + kk < K) ? A[static_cast<size_t>(m0 + r) * K + k0 + kk] : 0.f;
-            Bs[kk][r] = (n0 + r < N && k0 + kk < K) ? B[static_cast<size_t>(n0 + r) * K + k0 + kk] : 0.f;
+            As[kk][r] = (m0 + r < M && k0 + kk < K) ? A[static_cast<size_t>(m0 + r) * lda + k0 + kk] : 0.f;
+            Bs[kk][r] = (n0 + r < N && k0 + kk < K) ? sg_ldw(B + static_cast<size_t>(n0 + r) * K + k0 + kk) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -52,7 +57,7 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__
             if (n >= N) continue;
             float v = acc[i][j] + (bias ? bias[n] : 0.f);
             if (act == SG_SILU) v = v / (1.0f + expf(-v));
-            C[static_cast<size_t>(m) * N + n] = v;
+            C[static_cast<size_t>(m) * ldc + n] = v;
         }
     }
 }

@@ -1340,7 +1340,7 @@ inline int t2s_launch_decode(const covo_t2s* h, const T2SDecArgs& args, size_t s
 
 inline int t2s_sgemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t st) {
     ProfScope ps(PC_PROLOGUE, 2.0 * M * N * K, st);
-    sgemm_nt_kernel<<<dim3(ceil_div(N, 64), ceil_div(M, 64)), 256, 0, st>>>(A, W, bias, C, M, N, K, SG_NONE);
+    sgemm_nt_kernel<float><<<dim3(ceil_div(N, 64), ceil_div(M, 64)), 256, 0, st>>>(A, K, W, bias, C, N, M, N, K, SG_NONE);
     COVO_CK(cudaGetLastError());
     return COVO_OK;
 }
