@@ -39,6 +39,10 @@ WORKLOADS = {
                name="C3: VoMix 2-stream, 64 Euler steps (128 network passes), 30 s dialogue, batch 8, + HiFi-GAN"),
     "c2": dict(model="vosingle", B=1, N=650, prompt=150, method="euler", n_steps=32,
                name="C2: VoSingle, 32 Euler steps, 10 s monologue, batch 1, + HiFi-GAN"),
+    # C3's shape with the REFERENCE DEFAULT solver (acoustic.py:586-591: midpoint, step 1/16 = 32 NFE; SURVEY 8d "step-count naming")
+    "c3m": dict(model="vomix", B=8, N=1650, prompt=150, method="midpoint", n_steps=16,
+                name="C3 shape, reference-default solver: VoMix 2-stream, midpoint 16 steps (32 NFE, 64 network passes), 30 s dialogue, "
+                     "batch 8, + HiFi-GAN"),
     # BASELINE.json configs[3] per GPU: the full pipeline.  CoMix text-to-semantic (200 text tokens -> 1500 positions x 2
     # streams, EOS ignored: random-init weights would stop at a random position) -> VoMix (as C3) -> HiFi-GAN.
     "c4": dict(model="vomix", B=8, N=1650, prompt=150, method="euler", n_steps=64, t2s=dict(S=200, steps=1500),
@@ -114,18 +118,21 @@ class ClockSampler:
 
 def ncu_traffic_per_launch():
     """Mean DRAM read+write bytes per GEMM launch from the committed ncu --set full capture of this workload
-    (profiles/r01_gemm_c3_ncu.md, written by tools/summarize_ncu.py); None if the capture is not there."""
-    path = os.path.join(ROOT, "profiles", "r01_gemm_c3_ncu.md")
-    if not os.path.exists(path):
-        return None
-    vals = []
-    for ln in open(path):
-        if ln.startswith("- DRAM traffic"):
-            try:
-                vals.append(float(ln.split("=")[-1].split()[0]) * 1e6)
-            except ValueError:
-                pass
-    return sum(vals) / len(vals) if vals else None
+    (profiles/r0N_gemm_c3_ncu.md, newest round first; written by tools/summarize_ncu.py); (None, None) if there is no capture."""
+    for name in ("r02_gemm_c3_ncu.md", "r01_gemm_c3_ncu.md"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        vals = []
+        for ln in open(path):
+            if ln.startswith("- DRAM traffic"):
+                try:
+                    vals.append(float(ln.split("=")[-1].split()[0]) * 1e6)
+                except ValueError:
+                    pass
+        if vals:
+            return sum(vals) / len(vals), name
+    return None, None
 
 
 def config_for(wl, world, t2s_sms=0, flow_sms=None):
@@ -249,7 +256,7 @@ def run_b200(args):
     line = bench_workload(args, args.workload, ctx, detail=True)
     if args.workload == "c3" and not args.no_other_configs:
         others = {}
-        for key, steps in (("c2", 5), ("c4p", 2)):
+        for key, steps in (("c2", 5), ("c3m", 2), ("c4p", 2)):
             try:
                 sub = bench_workload(argparse.Namespace(**{**vars(args), "steps": steps, "no_cpu_baseline": True}), key, ctx,
                                      detail=False)
@@ -440,8 +447,8 @@ def bench_workload(args, wl_key, ctx, detail=True):
             "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM), launches of the velocity net's Linear layers",
             "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["tflops"], "peak_source": pk["src"],
-            "traffic": ncu_traffic_per_launch() if wl_key == "c3" else None,
-            "traffic_note": "mean dram__bytes_read+write per GEMM launch over the 8 launches of profiles/r01_gemm_c3_ncu.md (bytes)",
+            "traffic": ncu_traffic_per_launch()[0] if wl_key == "c3" else None,
+            "traffic_note": f"mean dram__bytes_read+write per GEMM launch over the launches of profiles/{ncu_traffic_per_launch()[1]} (bytes)",
             "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "algorithmic_flops_per_launch": g_flops / max(g_n, 1),
             "share_of_step_kernel_time": g_ms / total_kernel_ms if total_kernel_ms else None,
             "how": "one extra instrumented step after the timed region: CUDA events around every launch on the launching stream",

@@ -15,6 +15,7 @@
 // Zero "same" padding is applied per conv at the true sequence ends (rows outside [0, T) are forced to zero after every
 // conv), tile halos inside the sequence are simply recomputed.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace covo {
@@ -24,6 +25,9 @@ constexpr int HF_TP = 256;          // output samples per tile
 constexpr int HF_R = 384;           // rows computed per tile (multiple of 16)
 constexpr int HF_MARGIN = 32;       // zero rows before / after the operand buffers (>= max tap reach)
 constexpr int HF_LDA = 40;          // operand row stride in halves (80 B: ldmatrix conflict-free)
+constexpr int HF_LDX = 40;          // fp32 row stride of the residual stream: the conv2 epilogue's 8-byte accesses (lane = (row g, column
+                                    // pair q)) hit 32 g + 8 q mod 128 per half-warp -- conflict-free; a 32-float stride put all 8 rows of a
+                                    // fragment on the same banks (4-way conflicts on every read-modify-write of the residual)
 constexpr int HF_LDS = 33;          // fp32 row stride of the resblock sum (conv_post reads a row per thread)
 constexpr int HF_THREADS = 512;
 constexpr int HF_MT = 2;             // m-tiles per warp and conv: ceil((HF_R / 16) / (HF_THREADS / 32))
@@ -32,7 +36,7 @@ constexpr int HF_LDW = HF_MAXK * HF_C + 8;   // weight row stride in halves
 
 constexpr size_t hf_al(size_t x) { return (x + 127) / 128 * 128; }
 constexpr size_t HF_OFF_XR = 0;
-constexpr size_t HF_OFF_A1 = hf_al(HF_OFF_XR + sizeof(float) * HF_R * HF_C);
+constexpr size_t HF_OFF_A1 = hf_al(HF_OFF_XR + sizeof(float) * HF_R * HF_LDX);
 constexpr size_t HF_OFF_A2 = hf_al(HF_OFF_A1 + sizeof(uint16_t) * (HF_R + 2 * HF_MARGIN) * HF_LDA);
 constexpr size_t HF_OFF_SUM = hf_al(HF_OFF_A2 + sizeof(uint16_t) * (HF_R + 2 * HF_MARGIN) * HF_LDA);
 constexpr size_t HF_OFF_W1 = hf_al(HF_OFF_SUM + sizeof(float) * (HF_TP + 6) * HF_LDS);
@@ -80,16 +84,20 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
-__device__ __forceinline__ float lrelu_f(float v, float s) { return v > 0.f ? v : v * s; }
+__device__ __forceinline__ float lrelu_f(float v, float s) { return fmaxf(v, v * s); }      // 0 < s < 1 (checked by the host)
 
 // One Conv1d(32 -> 32, k, dilation d, "same") over rows [mt0*16, mt1*16) of the tile: A = operand rows (with margin),
-// W = weights [32][k*32] in smem.  epi(row, col, v0, v1) receives the pre-bias sums of two adjacent output channels.
-template <bool FP16, class Epi>
-__device__ __forceinline__ void hf_conv(const uint16_t* A, const uint16_t* W, int k, int d, int mt0, int mt1, Epi epi) {
+// W = weights [32][k*32] in smem.  epi(row, n_tile, col, v0, v1) receives the pre-bias sums of two adjacent output channels.
+// KT > 0: kernel size known at compile time -- the (tap, 16-channel) steps are fully unrolled and software-pipelined: the
+// ldmatrix fragments of step s+1 are requested before the MMAs of step s issue, so a warp keeps the tensor pipe fed on its own
+// (with three warps per sub-partition there is little else to hide the ~30-cycle ldmatrix latency).  KT = 0: generic loop.
+template <bool FP16, int KT, class Epi>
+__device__ __forceinline__ void hf_conv(const uint16_t* A, const uint16_t* W, int k_rt, int d, int mt0, int mt1, Epi epi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = HF_THREADS / 32;
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;      // ldmatrix address roles (A)
     const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;       // (B: two n-tiles per x4)
+    const int k = KT > 0 ? KT : k_rt;
     const int half = (k - 1) / 2;
     // a warp owns up to HF_MT consecutive m-tiles so that the weight fragments are reused
     const int per = (mt1 - mt0 + nwarps - 1) / nwarps;
@@ -100,23 +108,63 @@ __device__ __forceinline__ void hf_conv(const uint16_t* A, const uint16_t* W, in
     for (int i = 0; i < HF_MT; ++i)
 #pragma unroll
         for (int n = 0; n < 4; ++n) acc[i][n][0] = acc[i][n][1] = acc[i][n][2] = acc[i][n][3] = 0.f;
-    for (int tap = 0; tap < k; ++tap) {
-        const int shift = (tap - half) * d;
+    if (KT > 0) {
+        constexpr int S = 2 * (KT > 0 ? KT : 1);                  // steps: (tap, 16-channel half)
+        static_assert(HF_MT == 2, "the pipelined path is written for up to two m-tiles per warp");
+        const bool two = m_begin + 1 < m_end;                      // warp-uniform: does this warp own a second m-tile?
+        const uint16_t* wp0 = W + b_row * HF_LDW + b_col;
+        const uint16_t* ap0 = A + (HF_MARGIN + m_begin * 16 - half * d + a_row) * HF_LDA + a_col;
+        const int dstep = d * HF_LDA;
+        // the warp's m-tile count (1 or 2) is warp-uniform: two straight-line copies instead of a per-step predicate
+        // around the .sync.aligned instructions (which ptxas guards with WARPSYNC / BSSY pairs)
+        auto run = [&](auto mt_c) {
+            constexpr int MT = decltype(mt_c)::value;
+            uint32_t bq[2][8], aq[2][MT][4];
+            auto fetch = [&](int s, uint32_t (&bb)[8], uint32_t (&aa)[MT][4]) {
+                const int tap = s >> 1, ks = s & 1;
+                uint32_t (&b01)[4] = *reinterpret_cast<uint32_t (*)[4]>(&bb[0]);
+                uint32_t (&b23)[4] = *reinterpret_cast<uint32_t (*)[4]>(&bb[4]);
+                ldmatrix_x4(b01, wp0 + tap * HF_C + ks * 16);
+                ldmatrix_x4(b23, wp0 + tap * HF_C + ks * 16 + 16 * HF_LDW);
+                const uint16_t* ap = ap0 + tap * dstep + ks * 16;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            uint32_t b01[4], b23[4];
-            const uint16_t* wp = W + b_row * HF_LDW + tap * HF_C + ks * 16 + b_col;
-            ldmatrix_x4(b01, wp);                      // n-tiles 0, 1
-            ldmatrix_x4(b23, wp + 16 * HF_LDW);        // n-tiles 2, 3
+                for (int i = 0; i < MT; ++i) ldmatrix_x4(aa[i], ap + i * 16 * HF_LDA);
+            };
+            fetch(0, bq[0], aq[0]);
 #pragma unroll
-            for (int i = 0; i < HF_MT; ++i) {
-                if (m_begin + i < m_end) {
-                    uint32_t a[4];
-                    ldmatrix_x4(a, A + (HF_MARGIN + (m_begin + i) * 16 + shift + a_row) * HF_LDA + ks * 16 + a_col);
-                    mma_16816<FP16>(acc[i][0], a, b01[0], b01[1]);
-                    mma_16816<FP16>(acc[i][1], a, b01[2], b01[3]);
-                    mma_16816<FP16>(acc[i][2], a, b23[0], b23[1]);
-                    mma_16816<FP16>(acc[i][3], a, b23[2], b23[3]);
+            for (int s = 0; s < S; ++s) {
+                const int cur = s & 1;
+                if (s + 1 < S) fetch(s + 1, bq[cur ^ 1], aq[cur ^ 1]);
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    mma_16816<FP16>(acc[i][0], aq[cur][i], bq[cur][0], bq[cur][1]);
+                    mma_16816<FP16>(acc[i][1], aq[cur][i], bq[cur][2], bq[cur][3]);
+                    mma_16816<FP16>(acc[i][2], aq[cur][i], bq[cur][4], bq[cur][5]);
+                    mma_16816<FP16>(acc[i][3], aq[cur][i], bq[cur][6], bq[cur][7]);
+                }
+            }
+        };
+        if (two) run(std::integral_constant<int, 2>());
+        else run(std::integral_constant<int, 1>());
+    } else {
+        for (int tap = 0; tap < k; ++tap) {
+            const int shift = (tap - half) * d;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t b01[4], b23[4];
+                const uint16_t* wp = W + b_row * HF_LDW + tap * HF_C + ks * 16 + b_col;
+                ldmatrix_x4(b01, wp);                      // n-tiles 0, 1
+                ldmatrix_x4(b23, wp + 16 * HF_LDW);        // n-tiles 2, 3
+#pragma unroll
+                for (int i = 0; i < HF_MT; ++i) {
+                    if (m_begin + i < m_end) {
+                        uint32_t a[4];
+                        ldmatrix_x4(a, A + (HF_MARGIN + (m_begin + i) * 16 + shift + a_row) * HF_LDA + ks * 16 + a_col);
+                        mma_16816<FP16>(acc[i][0], a, b01[0], b01[1]);
+                        mma_16816<FP16>(acc[i][1], a, b01[2], b01[3]);
+                        mma_16816<FP16>(acc[i][2], a, b23[0], b23[1]);
+                        mma_16816<FP16>(acc[i][3], a, b23[2], b23[3]);
+                    }
                 }
             }
         }
@@ -128,8 +176,8 @@ __device__ __forceinline__ void hf_conv(const uint16_t* A, const uint16_t* W, in
             const int r = (m_begin + i) * 16 + g;
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-                epi(r, n * 8 + c2, acc[i][n][0], acc[i][n][1]);
-                epi(r + 8, n * 8 + c2, acc[i][n][2], acc[i][n][3]);
+                epi(r, n, n * 8 + c2, acc[i][n][0], acc[i][n][1]);
+                epi(r + 8, n, n * 8 + c2, acc[i][n][2], acc[i][n][3]);
             }
         }
     }
@@ -149,10 +197,56 @@ __device__ __forceinline__ void hf_load_weights(uint16_t* Ws, const void* wg, in
 }
 __device__ __forceinline__ void hf_wait_weights() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// The dilated-conv chain of resblock j over tile rows [mt0*16, mt1*16) (models.py:35-42); W1 must already be in flight.
+template <bool FP16, int KT>
+__device__ __forceinline__ void hf_resblock(const HifiFusedArgs& a, int j, int mt0, int mt1, int base, float* XR, uint16_t* A1,
+                                            uint16_t* A2, uint16_t* W1, uint16_t* W2) {
+    const int k = a.ksize[j];
+    const bool interior = base >= 0 && base + HF_R <= a.T;      // CTA-uniform: no row of the tile lies outside the sequence
+    auto in_seq = [&](int r) { const int gp = base + r; return interior || (gp >= 0 && gp < a.T); };
+    for (int m = 0; m < a.nd; ++m) {
+        hf_wait_weights();
+        __syncthreads();                              // W1 landed; A1 / XR of the previous step complete
+        hf_load_weights<FP16>(W2, a.w2[j][m], k);
+        // xt = lrelu(c1(lrelu(x)))                                  (models.py:36-38)
+        {
+            float2 bias[4];                                   // this lane's 4 column pairs (c = 8 n + 2 (lane & 3))
+#pragma unroll
+            for (int n = 0; n < 4; ++n) bias[n] = *reinterpret_cast<const float2*>(a.b1[j][m] + n * 8 + (threadIdx.x & 3) * 2);
+            const float slope = a.slope_res;
+            hf_conv<FP16, KT>(A1, W1, k, a.dil[j][m], mt0, mt1, [&](int r, int n, int c, float v0, float v1) {
+                uint32_t pk = 0u;
+                if (in_seq(r)) pk = pack_h2<FP16>(lrelu_f(v0 + bias[n].x, slope), lrelu_f(v1 + bias[n].y, slope));
+                *reinterpret_cast<uint32_t*>(A2 + (HF_MARGIN + r) * HF_LDA + c) = pk;
+            });
+        }
+        hf_wait_weights();
+        __syncthreads();                              // W2 landed; A2 complete; W1 free
+        if (m + 1 < a.nd) hf_load_weights<FP16>(W1, a.w1[j][m + 1], k);
+        // x = c2(xt) + x ; next operand lrelu(x)                    (models.py:39-41)
+        {
+            float2 bias[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) bias[n] = *reinterpret_cast<const float2*>(a.b2[j][m] + n * 8 + (threadIdx.x & 3) * 2);
+            const float slope = a.slope_res;
+            hf_conv<FP16, KT>(A2, W2, k, 1, mt0, mt1, [&](int r, int n, int c, float v0, float v1) {
+                float2 xv = make_float2(0.f, 0.f);
+                if (in_seq(r)) {
+                    const float2 old = *reinterpret_cast<const float2*>(XR + r * HF_LDX + c);
+                    xv = make_float2(v0 + bias[n].x + old.x, v1 + bias[n].y + old.y);
+                }
+                *reinterpret_cast<float2*>(XR + r * HF_LDX + c) = xv;
+                *reinterpret_cast<uint32_t*>(A1 + (HF_MARGIN + r) * HF_LDA + c) =
+                    pack_h2<FP16>(lrelu_f(xv.x, slope), lrelu_f(xv.y, slope));
+            });
+        }
+    }
+}
+
 template <bool FP16>
 __global__ void __launch_bounds__(HF_THREADS, 1) hifigan_fused_last_stage_kernel(const HifiFusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* XR = reinterpret_cast<float*>(smem_raw + HF_OFF_XR);          // [HF_R][32] fp32 residual stream
+    float* XR = reinterpret_cast<float*>(smem_raw + HF_OFF_XR);          // [HF_R][HF_LDX] fp32 residual stream
     uint16_t* A1 = reinterpret_cast<uint16_t*>(smem_raw + HF_OFF_A1);    // [HF_R + 2*margin][HF_LDA] lrelu(x)
     uint16_t* A2 = reinterpret_cast<uint16_t*>(smem_raw + HF_OFF_A2);    //  "  lrelu(conv1)
     float* SUM = reinterpret_cast<float*>(smem_raw + HF_OFF_SUM);        // [HF_TP + 6][HF_LDS]
@@ -187,51 +281,25 @@ __global__ void __launch_bounds__(HF_THREADS, 1) hifigan_fused_last_stage_kernel
             const int r = i / (HF_C / 4), c4 = (i % (HF_C / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (in_seq(r)) v = *reinterpret_cast<const float4*>(xg + static_cast<size_t>(base + r) * a.ldx + c4);
-            *reinterpret_cast<float4*>(XR + r * HF_C + c4) = v;
+            *reinterpret_cast<float4*>(XR + r * HF_LDX + c4) = v;
             uint2 pk;
             pk.x = pack_h2<FP16>(lrelu_f(v.x, a.slope_res), lrelu_f(v.y, a.slope_res));
             pk.y = pack_h2<FP16>(lrelu_f(v.z, a.slope_res), lrelu_f(v.w, a.slope_res));
             *reinterpret_cast<uint2*>(A1 + (HF_MARGIN + r) * HF_LDA + c4) = pk;
         }
         // weights stream through two buffers with cp.async: c2's arrive while c1 runs, the next c1's while c2 runs
-        for (int m = 0; m < a.nd; ++m) {
-            hf_wait_weights();
-            __syncthreads();                              // W1 landed; A1 / XR of the previous step complete
-            hf_load_weights<FP16>(W2, a.w2[j][m], k);
-            // xt = lrelu(c1(lrelu(x)))                                  (models.py:36-38)
-            {
-                const float* bias = a.b1[j][m];
-                const float slope = a.slope_res;
-                hf_conv<FP16>(A1, W1, k, a.dil[j][m], mt0, mt1, [&](int r, int c, float v0, float v1) {
-                    uint32_t pk = 0u;
-                    if (in_seq(r)) pk = pack_h2<FP16>(lrelu_f(v0 + bias[c], slope), lrelu_f(v1 + bias[c + 1], slope));
-                    *reinterpret_cast<uint32_t*>(A2 + (HF_MARGIN + r) * HF_LDA + c) = pk;
-                });
-            }
-            hf_wait_weights();
-            __syncthreads();                              // W2 landed; A2 complete; W1 free
-            if (m + 1 < a.nd) hf_load_weights<FP16>(W1, a.w1[j][m + 1], k);
-            // x = c2(xt) + x ; next operand lrelu(x)                    (models.py:39-41)
-            {
-                const float* bias = a.b2[j][m];
-                const float slope = a.slope_res;
-                hf_conv<FP16>(A2, W2, k, 1, mt0, mt1, [&](int r, int c, float v0, float v1) {
-                    float2 xv = make_float2(0.f, 0.f);
-                    if (in_seq(r)) {
-                        const float2 old = *reinterpret_cast<const float2*>(XR + r * HF_C + c);
-                        xv = make_float2(v0 + bias[c] + old.x, v1 + bias[c + 1] + old.y);
-                    }
-                    *reinterpret_cast<float2*>(XR + r * HF_C + c) = xv;
-                    *reinterpret_cast<uint32_t*>(A1 + (HF_MARGIN + r) * HF_LDA + c) =
-                        pack_h2<FP16>(lrelu_f(xv.x, slope), lrelu_f(xv.y, slope));
-                });
-            }
+        switch (k) {
+            case 3: hf_resblock<FP16, 3>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
+            case 5: hf_resblock<FP16, 5>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
+            case 7: hf_resblock<FP16, 7>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
+            case 11: hf_resblock<FP16, 11>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
+            default: hf_resblock<FP16, 0>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
         }
         __syncthreads();
         // xs += resblock output over the TP + 6 rows conv_post needs
         for (int i = tid; i < (HF_TP + 6) * HF_C; i += HF_THREADS) {
             const int r = i / HF_C, c = i % HF_C;
-            SUM[r * HF_LDS + c] += XR[(a.H + r) * HF_C + c];
+            SUM[r * HF_LDS + c] += XR[(a.H + r) * HF_LDX + c];
         }
     }
     __syncthreads();

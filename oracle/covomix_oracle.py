@@ -112,8 +112,9 @@ def time_embedding(sd: Dict[str, Tensor], times: Tensor) -> Tensor:
 
 def rotary_table(sd: Dict[str, Tensor], n: int) -> Tensor:
     """RotaryEmbedding.forward (acoustic.py:126-130): freqs[n, j] duplicated to dim_head."""
-    t = torch.arange(n, dtype=torch.float32)
-    freqs = torch.einsum("i,j->ij", t, sd["transformer.rotary_emb.inv_freq"])
+    inv_freq = sd["transformer.rotary_emb.inv_freq"]
+    t = torch.arange(n, dtype=torch.float32, device=inv_freq.device)
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
     return torch.cat((freqs, freqs), dim=-1)
 
 
@@ -141,7 +142,7 @@ def attention(sd: Dict[str, Tensor], prefix: str, x: Tensor, rotary: Tensor, hea
     q, k = apply_rotary(rotary, q), apply_rotary(rotary, k)
     sim = torch.einsum("bhid,bhjd->bhij", q, k) * (q.shape[-1] ** -0.5)
     attn = sim.softmax(dim=-1)
-    out = torch.einsum("bhij,bhjd->bhid", attn, v)
+    out = torch.einsum("bhij,bhjd->bhid", attn.to(v.dtype), v)      # (.to: no-op in fp32; lets tests run this under autocast)
     out = out.permute(0, 2, 1, 3).reshape(B, N, -1)
     return F.linear(out, sd[prefix + ".to_out.weight"])
 

@@ -14,5 +14,8 @@ unset COVO_NO_GRAPH
 # vocoder at the bench shape [8, 80, 1500]: DRAM bytes of every launch of one forward (metrics only: fast)
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file gpurun_out/voc_dram.csv python tools/vocoder_bench.py one > gpurun_out/voc_under_ncu.log 2>&1
+# the fused last vocoder stage at the bench shape (51 tiles per SM, not the wave-tail case B = 1, T = 256)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hifigan_fused -s 2 -c 1 -o gpurun_out/hifigan_fused -f \
+    python tools/vocoder_bench.py one > /dev/null 2>&1
 timeout 300 python tools/attn_one.py | tee gpurun_out/attn_one.log
 ls -la gpurun_out | tail -20
