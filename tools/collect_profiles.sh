@@ -18,3 +18,6 @@ cp gpurun_out/parity_numbers.jsonl profiles/${R}_parity_numbers.jsonl
 cp gpurun_out/pytest_gpu.log profiles/${R}_pytest_gpu.log
 python tools/sass_tally.py > profiles/${R}_sass_tally.md
 ls profiles | grep ${R}
+# 8-GPU evidence (tools/gpu_round_8gpu.sh), when present
+for f in bench_c4p_8gpu.json bench_c3_8gpu.json; do [ -s gpurun_out/$f ] && cp gpurun_out/$f profiles/${R}_$f; done
+[ -s gpurun_out/bench_c5_8gpu.jsonl ] && cp gpurun_out/bench_c5_8gpu.jsonl profiles/${R}_bench_c5_vocoder_sweep_8gpu.jsonl
