@@ -61,6 +61,8 @@ struct AttnArgs {
     int n_pair_items;      // n_pairs * heads * sequences
     int n_items;           // + one single-group item per (sequence, head) when ceil(N / 128) is odd
     int stagger;           // != 0: exponential token between the two query groups (anti-phase); 0: free running
+    int sequences;         // Bt
+    int reverse;           // != 0: sequences are walked from the last to the first (serpentine order along the kernel chain)
 };
 
 inline void attn_fill_items(AttnArgs& a, int sequences) {
@@ -68,6 +70,7 @@ inline void attn_fill_items(AttnArgs& a, int sequences) {
     a.n_pairs = groups / 2;
     a.n_pair_items = a.n_pairs * a.heads * sequences;
     a.n_items = a.n_pair_items + (groups & 1) * a.heads * sequences;
+    a.sequences = sequences;
 }
 
 struct AttnItem {
@@ -86,7 +89,7 @@ __device__ __forceinline__ AttnItem attn_decode(const AttnArgs& args, int w) {
         it.two = 0;
     }
     it.head = r % args.heads;
-    it.seq = r / args.heads;
+    it.seq = args.reverse ? args.sequences - 1 - r / args.heads : r / args.heads;
     return it;
 }
 

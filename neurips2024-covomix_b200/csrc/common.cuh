@@ -397,6 +397,7 @@ inline int attn_build_args(AttnArgs& a, const void* qkv, void* out, int Bt, int 
     a.heads = heads;
     a.inner = inner;
     a.stagger = attn_tune().stagger;
+    a.reverse = 0;
     attn_fill_items(a, Bt);
     return COVO_OK;
 }

@@ -81,6 +81,7 @@ int covo_flow_create(const covo_flow_cfg* cfg, const void* packed_weights, size_
     if (const char* v = getenv("COVO_FLOW_PERSISTENT_ROWS")) h->persistent_max_rows = atoi(v);
     if (const char* v = getenv("COVO_FLOW_PERSISTENT_BN")) h->persistent_bn = atoi(v);
     h->naive_attn = env_flag("COVO_DEBUG_NAIVE_ATTN");
+    if (const char* v = getenv("COVO_FLOW_SERPENTINE")) h->serpentine = atoi(v) != 0;
     *out = h;
     return COVO_OK;
 }

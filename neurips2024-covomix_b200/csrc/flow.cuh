@@ -78,6 +78,7 @@ struct covo_flow {
     int persistent_max_rows = 4096;
     int persistent_bn = 0;         // COVO_FLOW_PERSISTENT_BN: force the GEMM tile width of the persistent path (0: heuristic)
     float step_size = 0.f;         // covo_flow_set_step_size: torchdiffeq grid k*h with the last point snapped to 1
+    int serpentine = 1;            // COVO_FLOW_SERPENTINE: alternate the row order from kernel to kernel (flow_enqueue_network)
 };
 
 namespace covo {
@@ -290,7 +291,7 @@ inline int flow_build_ops(covo_flow* h, FlowPlan& p) {
     return COVO_OK;
 }
 
-inline int launch_attention(const covo_flow* h, const FlowPlan& p, cudaStream_t st) {
+inline int launch_attention(const covo_flow* h, const FlowPlan& p, cudaStream_t st, int rev = 0) {
     const int Bt = p.M / p.N;
     ProfScope ps(PC_ATTN, 4.0 * p.N * static_cast<double>(p.N) * h->cfg.dim_head * h->cfg.heads * Bt, st);
     if (h->naive_attn) {
@@ -298,23 +299,25 @@ inline int launch_attention(const covo_flow* h, const FlowPlan& p, cudaStream_t 
         naive_attention_kernel<<<grid, 256, 0, st>>>(p.qkv, p.attn_o, p.N, h->cfg.heads, p.attn.inner,
                                                      1.0f / sqrtf(static_cast<float>(h->cfg.dim_head)));
     } else {
-        COVO_TRY(launch_attention_kernel(p.attn, h->di.num_sms, st));
+        AttnArgs a = p.attn;
+        a.reverse = rev;
+        COVO_TRY(launch_attention_kernel(a, h->di.num_sms, st));
     }
     COVO_CK(cudaGetLastError());
     return COVO_OK;
 }
 
 template <int V>
-inline void launch_rmsnorm_v(const float* x, const float* g, const float* b, __nv_bfloat16* out, int M, cudaStream_t st) {
-    rmsnorm_kernel<V><<<ceil_div(M, 8), 256, 0, st>>>(x, g, b, out, M);
+inline void launch_rmsnorm_v(const float* x, const float* g, const float* b, __nv_bfloat16* out, int M, int rev, cudaStream_t st) {
+    rmsnorm_kernel<V><<<ceil_div(M, 8), 256, 0, st>>>(x, g, b, out, M, rev);
 }
-inline int launch_rmsnorm(const float* x, const float* g, const float* b, __nv_bfloat16* out, int M, int D, cudaStream_t st) {
+inline int launch_rmsnorm(const float* x, const float* g, const float* b, __nv_bfloat16* out, int M, int D, int rev, cudaStream_t st) {
     ProfScope ps(PC_NORM, 0.0, st);
     switch (D / 128) {
-        case 8: launch_rmsnorm_v<8>(x, g, b, out, M, st); break;
-        case 4: launch_rmsnorm_v<4>(x, g, b, out, M, st); break;
-        case 2: launch_rmsnorm_v<2>(x, g, b, out, M, st); break;
-        case 1: launch_rmsnorm_v<1>(x, g, b, out, M, st); break;
+        case 8: launch_rmsnorm_v<8>(x, g, b, out, M, rev, st); break;
+        case 4: launch_rmsnorm_v<4>(x, g, b, out, M, rev, st); break;
+        case 2: launch_rmsnorm_v<2>(x, g, b, out, M, rev, st); break;
+        case 1: launch_rmsnorm_v<1>(x, g, b, out, M, rev, st); break;
         default: return fail(COVO_ERR_INVALID, "dim %d unsupported by rmsnorm (need 128/256/512/1024)", D);
     }
     COVO_CK(cudaGetLastError());
@@ -375,28 +378,40 @@ inline int flow_enqueue_network(covo_flow* h, FlowPlan& p, int t_idx, cudaStream
         // 32 positions per thread: 62 window loads per 32 outputs (1.9x read amplification; 8 per thread was 4.75x)
         constexpr int CONVPOS_TB = 32;
         dim3 g(ceil_div(D, 256), ceil_div(p.N, CONVPOS_TB), Bt);
-        convpos_kernel<31, CONVPOS_TB><<<g, 256, 0, st>>>(p.h0, h->conv_wT.as<float>(), h->conv_b.as<float>(), p.x, p.slots, p.N, D);
+        convpos_kernel<31, CONVPOS_TB><<<g, 256, 0, st>>>(p.h0, h->conv_wT.as<float>(), h->conv_b.as<float>(), p.x, p.slots, p.N, D,
+                                                          h->serpentine);
         COVO_CK(cudaGetLastError());
     }
     *launches += 2;
     const float* gb_t = p.gb + static_cast<size_t>(t_idx) * c.depth * 4 * D;
+    // Serpentine row order along the chain (COVO_FLOW_SERPENTINE, default on): every kernel walks the token rows in the
+    // opposite direction of its producer, so it starts on the rows that were written LAST and are still in L2.  The
+    // activations of a C3 pass (x 108 MB fp32, a_norm 54, qkv 162, ffh 216 MB) are each about the size of the 126 MB L2: in
+    // producer order a consumer finds its first rows evicted already, LRU-thrashing through the whole tensor.
+    int dir = h->serpentine;                          // to_embed ran ascending, the conv-pos kernel descending
+    auto turn = [&]() { dir = h->serpentine ? dir ^ 1 : 0; return dir; };
+    auto gemm_dir = [&](const GemmOp& op) -> int {
+        GemmOp o = op;
+        o.args.reverse = turn();
+        return launch_gemm(o, st);
+    };
     for (int L = 0; L < c.depth; ++L) {
         const float* gbl = gb_t + static_cast<size_t>(L) * 4 * D;
         if (L >= half) {
-            COVO_TRY(launch_gemm(p.op_skip[L], st));
+            COVO_TRY(gemm_dir(p.op_skip[L]));
             ++*launches;
         }
-        COVO_TRY(launch_rmsnorm(p.x, gbl, gbl + D, p.a_norm, M, D, st));
-        COVO_TRY(launch_gemm(p.op_qkv[L], st));
-        COVO_TRY(launch_attention(h, p, st));
-        COVO_TRY(launch_gemm(p.op_out[L], st));
-        COVO_TRY(launch_rmsnorm(p.x, gbl + 2 * D, gbl + 3 * D, p.a_norm, M, D, st));
-        COVO_TRY(launch_gemm(p.op_ff1[L], st));
-        COVO_TRY(launch_gemm(p.op_ff2[L], st));
+        COVO_TRY(launch_rmsnorm(p.x, gbl, gbl + D, p.a_norm, M, D, turn(), st));
+        COVO_TRY(gemm_dir(p.op_qkv[L]));
+        COVO_TRY(launch_attention(h, p, st, turn()));
+        COVO_TRY(gemm_dir(p.op_out[L]));
+        COVO_TRY(launch_rmsnorm(p.x, gbl + 2 * D, gbl + 3 * D, p.a_norm, M, D, turn(), st));
+        COVO_TRY(gemm_dir(p.op_ff1[L]));
+        COVO_TRY(gemm_dir(p.op_ff2[L]));
         *launches += 7;
     }
-    COVO_TRY(launch_rmsnorm(p.x, h->final_gamma.as<float>(), nullptr, p.a_norm, M, D, st));
-    COVO_TRY(launch_gemm(p.op_pred, st));
+    COVO_TRY(launch_rmsnorm(p.x, h->final_gamma.as<float>(), nullptr, p.a_norm, M, D, turn(), st));
+    COVO_TRY(gemm_dir(p.op_pred));
     *launches += 2;
     return COVO_OK;
 }

@@ -70,6 +70,8 @@ struct GemmArgs {
     int scatter_c_valid;             // scatter path: only channels (n % phase_w) < scatter_c_valid are stored (0: all)
     float* out_f32;
     void* out_h;
+    int reverse;                     // != 0: the persistent schedule walks the tiles from the last to the first (serpentine order
+                                     // along a chain of kernels: what the previous kernel wrote last is read first, out of L2)
 };
 
 // Debug timeline of gemm_run (CTA 0 only; null in production): [0] entry, [1] barriers initialised, [2] first stage landed,
@@ -192,8 +194,9 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
             int s = 0;
             uint32_t ph = 0;
             for (int tile = cta; tile < total_tiles; tile += n_ctas) {
-                const int n_idx = tile % args.n_tiles;
-                const int mz = tile / args.n_tiles;
+                const int tt = args.reverse ? total_tiles - 1 - tile : tile;
+                const int n_idx = tt % args.n_tiles;
+                const int mz = tt / args.n_tiles;
                 const int m_idx = (mz % m_tiles_per_z) * MC + crank;
                 const int z = mz / m_tiles_per_z;
                 const int q0 = m_idx * GEMM_BM;
@@ -286,8 +289,9 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
         const bool use_tma = args.scatter == 0;
         const bool has_res = args.has_residual != 0;
         for (int tile = cta; tile < total_tiles; tile += n_ctas) {
-            const int n_idx = tile % args.n_tiles;
-            const int mz = tile / args.n_tiles;
+            const int tt = args.reverse ? total_tiles - 1 - tile : tile;
+            const int n_idx = tt % args.n_tiles;
+            const int mz = tt / args.n_tiles;
             const int m_idx = (mz % m_tiles_per_z) * MC + crank;
             const int z = mz / m_tiles_per_z;
             const int q_warp0 = m_idx * GEMM_BM + lq * 32;
@@ -392,7 +396,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                                     if (sp == 0 && ncol + 32 < args.n_valid) nn = ncol + 32;
                                     else if (c + 1 < NCH && ncol0 + 64 < args.n_valid) nn = ncol0 + 64;
                                     else if (tile + n_ctas < total_tiles) {
-                                        const int t2 = tile + n_ctas;
+                                        const int t2 = args.reverse ? total_tiles - 1 - (tile + n_ctas) : tile + n_ctas;
                                         const int mz2 = t2 / args.n_tiles;
                                         nq = ((mz2 % m_tiles_per_z) * MC + crank) * GEMM_BM + lq * 32;
                                         nz = mz2 / m_tiles_per_z;

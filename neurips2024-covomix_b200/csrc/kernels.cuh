@@ -112,12 +112,13 @@ __global__ void embed_input_kernel(const long long* __restrict__ ids, const floa
 // h, x: fp32 [Bt, N, D]; also writes the bf16 copy of x (the U-Net skip operand of layer 0).
 // Each thread: one channel, TB consecutive positions, sliding window in registers.
 template <int KS, int TB>
-__global__ void __launch_bounds__(256) convpos_kernel(const float* __restrict__ h, const float* __restrict__ wT /*[KS][D]*/,
+__global__ void __launch_bounds__(256, 2) convpos_kernel(const float* __restrict__ h, const float* __restrict__ wT /*[KS][D]*/,
                                                       const float* __restrict__ bias, float* __restrict__ x,
-                                                      __nv_bfloat16* __restrict__ x_h, int N, int D) {
+                                                      __nv_bfloat16* __restrict__ x_h, int N, int D, int reverse) {
+    // reverse: last sequence / last positions first (serpentine order after the to_embed GEMM, see flow_enqueue_network)
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n0 = blockIdx.y * TB;
-    const int b = blockIdx.z;
+    const int n0 = (reverse ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y)) * TB;
+    const int b = reverse ? static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z) : static_cast<int>(blockIdx.z);
     if (c >= D) return;
     const float* hb = h + static_cast<size_t>(b) * N * D + c;
     float w[KS];
@@ -146,12 +147,15 @@ __global__ void __launch_bounds__(256) convpos_kernel(const float* __restrict__ 
 
 // AdaptiveRMSNorm / RMSNorm (acoustic.py:174-175, :198-204): out = x / max(||x||, 1e-12) * sqrt(D) * gamma (+ beta),
 // written as the bf16 A operand of the next GEMM.  One warp per row, D = 32 * 4 * V.
+// reverse != 0: blocks walk the rows from the last to the first -- the rows the producer kernel wrote LAST are still in L2
+// (x is 108 MB at C3, the L2 126 MB: in producer order the consumer would find its first rows already evicted).
 template <int V>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
-                                                      int M) {
+                                                      int M, int reverse) {
     constexpr int D = 128 * V;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int blk = reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+    const int row = blk * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);

@@ -440,6 +440,25 @@ def test_persistent_step_kernel_matches_launch_per_op_path(dev, vosingle, method
     per_smp.close()
 
 
+def test_serpentine_row_order_is_pure_scheduling(dev, vomix):
+    """COVO_FLOW_SERPENTINE (default on): every kernel of the velocity net walks the token rows in the opposite direction of
+    its producer so that it starts on the rows still in L2.  Only the order of tiles / items / rows changes, never the
+    arithmetic inside one: results are bit-identical to the ascending order."""
+    sd, _ = vomix
+    up = _fresh_sampler(dev, sd, syn.VOMIX, {"COVO_FLOW_SERPENTINE": "0"}, torchdiffeq_ode_method="euler", ode_step_size=0.25)
+    sp = _fresh_sampler(dev, sd, syn.VOMIX, {"COVO_FLOW_SERPENTINE": "1"}, torchdiffeq_ode_method="euler", ode_step_size=0.25)
+    for B, N in ((3, 300), (1, 129), (2, 1)):
+        ids, cond, y0, _ = syn.synthetic_flow_inputs(syn.VOMIX, B, N, prompt=min(30, N), seed=12)
+        a = up.velocity(y0.to(dev), times=0.3, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+        b = sp.velocity(y0.to(dev), times=0.3, phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7)
+        assert torch.equal(a, b)
+        sa = up.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+        sb = sp.sample(phoneme_ids=ids.to(dev), cond=cond.to(dev), cond_scale=0.7, y0=y0.to(dev))
+        assert torch.isfinite(sb).all() and torch.equal(sa, sb)
+    up.close()
+    sp.close()
+
+
 def test_cluster_pair_gemm_path_matches(dev, vosingle):
     """COVO_GEMM_MC=2: GEMMs as cluster pairs with a multicast weight tile (gemm_tc_pair_kernel) -- same arithmetic."""
     sd, smp = vosingle
