@@ -145,8 +145,12 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // BN = 64: one 64-column chunk per lane quarter -> only 4 of the 8 epilogue warps have work
-    constexpr int EPI_WARPS_ACTIVE = (BN >= 128) ? GEMM_EPI_WARPS : 4;
+    // BN >= 128: the 8 epilogue warps share every tile (two per TMEM lane quarter, half of the columns each).  BN = 64: a tile has
+    // one 64-column chunk per lane quarter, so the warps form two SETS of four that take alternate tiles -- set s drains
+    // accumulator buffer s -- and two tiles' epilogues run side by side (the narrow vocoder stages are epilogue-bound: a
+    // 128 x 64 x 192 main loop is ~400 cycles against a ~4 000-cycle epilogue; with one set the 62-channel convs took 123-222 us).
+    constexpr int EPI_WARPS_ACTIVE = (BN >= 128) ? GEMM_EPI_WARPS : 4;        // arrivals per accumulator buffer
+    constexpr int EPI_TSTEP = (BN >= 128) ? 1 : 2;                            // tiles between two visits of an epilogue warp
 
     // MC == 2: the schedule runs over PAIR tiles (two M tiles x one N tile); `cta` / `n_ctas` then count clusters, and
     // m_tiles_per_z counts pairs (an odd tail pair has a phantom second tile: TMA zero-fills it, nothing is stored)
@@ -266,12 +270,13 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
-    } else if (ROLE != 1 && warp >= epi_warp0 && warp - epi_warp0 < EPI_WARPS_ACTIVE) {
+    } else if (ROLE != 1 && warp >= epi_warp0 && warp - epi_warp0 < GEMM_EPI_WARPS) {
         // ===================================================== epilogue warps
         // warp e = warp - epi_warp0: TMEM lane quarter lq = warp % 4 (hardware restriction), column half = e / 4.
         const int e = warp - epi_warp0;
         const int lq = warp & 3;
-        const int chalf = e >> 2;
+        const int chalf = (BN >= 128) ? (e >> 2) : 0;
+        const int eset = (BN >= 128) ? 0 : (e >> 2);          // BN = 64: which of the two warp sets (== accumulator buffer)
         constexpr int NB = Cfg::EPI_BUFS;
         uint8_t* buf = staging + e * NB * GEMM_EPI_BUF_BYTES;     // NB x [32 rows][128 B]; 16-B chunk c of row r at (c ^ (r&7))*16
         uint8_t* my_row = buf + lane * 128;
@@ -282,13 +287,13 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
         // NB = 2: fp32 sub-tile step k of this warp uses buffer k & 1; `pre`: the residual of step kstep has been requested
         uint32_t kstep = 0, kh = 0;
         bool pre = false;
-        int as = 0;
+        int as = eset;
         uint32_t aph = 0;
         constexpr int COLS_PER_WARP = (BN >= 128) ? BN / 2 : BN;
         constexpr int NCH = COLS_PER_WARP / 64;
         const bool use_tma = args.scatter == 0;
         const bool has_res = args.has_residual != 0;
-        for (int tile = cta; tile < total_tiles; tile += n_ctas) {
+        for (int tile = cta + eset * n_ctas; tile < total_tiles; tile += EPI_TSTEP * n_ctas) {
             const int tt = args.reverse ? total_tiles - 1 - tile : tile;
             const int n_idx = tt % args.n_tiles;
             const int mz = tt / args.n_tiles;
@@ -395,8 +400,8 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                                     int nq = q_warp0, nz = z, nn = -1;                 // the next fp32 sub-tile of this warp
                                     if (sp == 0 && ncol + 32 < args.n_valid) nn = ncol + 32;
                                     else if (c + 1 < NCH && ncol0 + 64 < args.n_valid) nn = ncol0 + 64;
-                                    else if (tile + n_ctas < total_tiles) {
-                                        const int t2 = args.reverse ? total_tiles - 1 - (tile + n_ctas) : tile + n_ctas;
+                                    else if (tile + EPI_TSTEP * n_ctas < total_tiles) {
+                                        const int t2 = args.reverse ? total_tiles - 1 - (tile + EPI_TSTEP * n_ctas) : tile + EPI_TSTEP * n_ctas;
                                         const int mz2 = t2 / args.n_tiles;
                                         nq = ((mz2 % m_tiles_per_z) * MC + crank) * GEMM_BM + lq * 32;
                                         nz = mz2 / m_tiles_per_z;
@@ -590,7 +595,11 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                     __syncwarp();
                 }
             }
-            if (++as == 2) { as = 0; aph ^= 1; }
+            if (BN >= 128) {
+                if (++as == 2) { as = 0; aph ^= 1; }
+            } else {
+                aph ^= 1;                                  // this set's buffer is used by every second tile
+            }
         }
         if (e == 0 && lane == 0) GTR(5);
         if (lane == 0) bulk_wait_all();      // smem must stay valid (and the output be complete) when the caller moves on

@@ -18,4 +18,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:hifigan_fused -s 2 -c 1 -o gpurun_out/hifigan_fused -f \
     python tools/vocoder_bench.py one > /dev/null 2>&1
 timeout 300 python tools/attn_one.py | tee gpurun_out/attn_one.log
+# summarise on the box and drop the reports (gpurun copies back at most 64 MiB); the GEMM report is kept for the source page
+for k in gemm_c3 attn_c3 hifigan_fused; do
+  [ -s gpurun_out/$k.ncu-rep ] && python tools/summarize_ncu.py full gpurun_out/$k.ncu-rep gpurun_out/${k}_ncu.md > /dev/null
+done
+python tools/summarize_ncu.py launches gpurun_out/launches.csv gpurun_out/launches_c3.md > /dev/null
+python tools/summarize_ncu.py dram gpurun_out/voc_dram.csv gpurun_out/vocoder_dram_ncu.md > /dev/null
+rm -f gpurun_out/attn_c3.ncu-rep gpurun_out/hifigan_fused.ncu-rep
 ls -la gpurun_out | tail -20

@@ -59,5 +59,45 @@ def full(path, out):
     print(open(out).read()[:6000])
 
 
+def dram(path, out):
+    """Per-launch time + DRAM bytes of one vocoder forward (ncu --metrics gpu__time_duration.sum,dram__bytes_*): by kernel."""
+    rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("==")) if r]
+    hdr = rows[0]
+    iid, ik, im, iu, iv = (hdr.index(k) for k in ("ID", "Kernel Name", "Metric Name", "Metric Unit", "Metric Value"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
+    per = OrderedDict()
+    for r in rows[1:]:
+        if len(r) <= iv:
+            continue
+        d = per.setdefault(r[iid], {"name": r[ik].split("(")[0].replace("void ", "").replace("covo::", "")})
+        d[r[im]] = float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
+    launches_ = list(per.values())
+    # the capture holds warm-up forwards too: keep the LAST forward (from the last mel_to_tc_kernel on)
+    starts = [i for i, d in enumerate(launches_) if d["name"].startswith("mel_to_tc")]
+    if starts:
+        launches_ = launches_[starts[-1]:]
+    agg = OrderedDict()
+    for d in launches_:
+        a = agg.setdefault(d["name"], [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += d.get("gpu__time_duration.sum", 0.0)
+        a[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+    t_us = sum(a[1] for a in agg.values())
+    by = sum(a[2] for a in agg.values())
+    with open(out, "w") as f:
+        f.write("# HiFi-GAN forward at [8, 80, 1500]: ncu per-launch time and DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum,\n"
+                "# --clock-control none; launches serialised by the profiler, so times are per-kernel, not the graph's)\n\n")
+        f.write(f"source: `{path}`; last forward of the capture: {len(launches_)} launches, {t_us:.0f} us, {by/1e9:.2f} GB of DRAM traffic "
+                f"= {by/1e3/t_us:.0f} GB/s averaged over the kernels' own time\n\n| kernel | launches | us | DRAM GB | GB/s |\n|---|---:|---:|---:|---:|\n")
+        for k, (n, us, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {n} | {us:.1f} | {b/1e9:.3f} | {b/1e3/max(us,1e-9):.0f} |\n")
+        f.write("\nper launch (time order):\n\n| # | kernel | us | DRAM MB | GB/s |\n|---:|---|---:|---:|---:|\n")
+        for i, d in enumerate(launches_):
+            b = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+            us = d.get("gpu__time_duration.sum", 0.0)
+            f.write(f"| {i} | `{d['name']}` | {us:.1f} | {b/1e6:.1f} | {b/1e3/max(us,1e-9):.0f} |\n")
+    print(open(out).read()[:3000])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "dram": dram}[sys.argv[1]](sys.argv[2], sys.argv[3])
