@@ -86,9 +86,10 @@ int covo_flow_velocity(covo_flow* h, const int64_t* ids, const float* cond, cons
 /* Number of kernels one covo_flow_sample call launches for this configuration (bench.py's gpu_launches). */
 int covo_flow_launches_per_sample(const covo_flow* h, int method, int n_steps, float cond_scale);
 
-/* Kernels launched by the most recent covo_flow_sample call on this handle.  Short utterances (2*B*N <= 4096 rows) run
- * every evaluation and solver update of the call inside ONE persistent cooperative kernel (csrc/flow_persistent.cuh), so
- * the count is then 9 (the per-call prologue + that kernel) instead of covo_flow_launches_per_sample. */
+/* Kernels launched by the most recent covo_flow_sample call on this handle.  With COVO_FLOW_PERSISTENT=1 (opt-in: measured
+ * slower than the CUDA graph) every evaluation and solver update of the call runs inside ONE persistent
+ * cooperative kernel (csrc/flow_persistent.cuh);
+ * the count is then 4 (embedding gather, e_const GEMM, state -> input, that kernel) instead of covo_flow_launches_per_sample. */
 int covo_flow_last_launches(const covo_flow* h);
 
 /* ---- HiFi-GAN generator ---------------------------------------------------------------------------

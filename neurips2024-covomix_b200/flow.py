@@ -134,7 +134,7 @@ class B200FlowSampler:
         return v
 
     def last_launches(self) -> int:
-        """Kernels launched by the most recent ``sample`` call (9 on the persistent path, else launches_per_sample)."""
+        """Kernels launched by the most recent ``sample`` call (4 on the persistent path, else launches_per_sample)."""
         return nat.lib().covo_flow_last_launches(self._h)
 
     def launches_per_sample(self, cond_scale: float = 0.7) -> int:
