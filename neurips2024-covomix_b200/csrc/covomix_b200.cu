@@ -200,6 +200,7 @@ int covo_hifigan_create(const covo_hifigan_cfg* cfg, const void* packed_weights,
         delete h;
         return rc;
     }
+    if (const char* v = getenv("COVO_GEMM_CG")) h->di.gemm_cg = atoi(v);       // A/B switch, as for the flow handle
     *out = h;
     return COVO_OK;
 }

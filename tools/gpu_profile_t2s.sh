@@ -8,4 +8,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 7
 unset COVO_NO_GRAPH
 T2S_FMTS=bf16 T2S_B=8 timeout 900 ncu --set full --clock-control none --import-source on -k regex:t2s_decode -s 1 -c 1 \
     -o gpurun_out/t2s_decode python tools/t2s_bench.py comix 200 > gpurun_out/t2s_under_ncu.log 2>&1
+python tools/summarize_ncu.py launches gpurun_out/launches_c4.csv gpurun_out/launches_c4.md > /dev/null
+python tools/summarize_ncu.py full gpurun_out/t2s_decode.ncu-rep gpurun_out/t2s_decode_ncu.md > /dev/null
+rm -f gpurun_out/t2s_decode.ncu-rep
 ls -la gpurun_out
