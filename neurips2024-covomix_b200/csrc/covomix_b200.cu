@@ -201,6 +201,13 @@ int covo_hifigan_create(const covo_hifigan_cfg* cfg, const void* packed_weights,
         return rc;
     }
     if (const char* v = getenv("COVO_GEMM_CG")) h->di.gemm_cg = atoi(v);       // A/B switch, as for the flow handle
+    rc = hifi_build_aligned_upconvs(h);
+    if (rc != COVO_OK) {
+        for (void* q : h->up_al) if (q) cudaFree(q);
+        h->w.release();
+        delete h;
+        return rc;
+    }
     *out = h;
     return COVO_OK;
 }
@@ -210,6 +217,7 @@ int covo_hifigan_destroy(covo_hifigan* h) {
     DeviceGuard g(h->di.device);
     cudaDeviceSynchronize();
     for (HifiPlan* p : h->plans) delete p;
+    for (void* q : h->up_al) if (q) cudaFree(q);
     h->w.release();
     delete h;
     return COVO_OK;

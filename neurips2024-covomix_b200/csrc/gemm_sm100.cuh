@@ -15,13 +15,14 @@
 // TMEM -> registers (thread = row) -> [RoPE] -> + bias -> + residual (sub-tile TMA-loaded into smem)
 // -> fp32 sub-tile into 128B-swizzled smem -> TMA store; and/or activation -> bf16/fp16 -> smem -> TMA
 // store.  All global traffic of the epilogue is bulk-asynchronous; TMA clips rows/columns that fall
-// outside the output tensor.  ConvTranspose1d outputs (row q, column n -> sample stride*q + n/C - pad)
-// do not form a box and use a per-element store path instead.
+// outside the output tensor.  ConvTranspose1d in the classic polyphase form (row q, column n -> sample
+// stride*q + n/C - pad) does not form a box and uses a per-element store path; the vocoder plan re-indexes
+// the weights into an aligned polyphase form wherever k - 2 pad == stride (hifigan.cuh), which does.
 //
 // The same kernel serves every dense contraction on the hot path: the velocity net's Linear layers
 // (taps = 1), its U-Net skip combiner (taps = 2 over two activation slots), HiFi-GAN's dilated
 // Conv1d (taps = kernel size, tap_row = k*dilation - pad) and ConvTranspose1d (polyphase:
-// N = stride*Cout, taps = ceil(K/stride), tap_row = -j).
+// N = stride*Cout, taps = ceil(K/stride) (+1 in the aligned form), tap_row = -j).
 #pragma once
 #include "ptx.cuh"
 
@@ -67,7 +68,8 @@ struct GemmArgs {
     int scatter;
     long long out_zs, out_rs, out_off;
     int up_s, up_p, phase_w, t_out;
-    int scatter_c_valid;             // scatter path: only channels (n % phase_w) < scatter_c_valid are stored (0: all)
+    int scatter_c_valid;             // only columns with (n % phase_w) < scatter_c_valid are stored (0: all): the ConvTranspose1d in
+                                     // front of the fused last vocoder stage writes just the channels that stage reads
     float* out_f32;
     void* out_h;
     int reverse;                     // != 0: the persistent schedule walks the tiles from the last to the first (serpentine order
@@ -392,7 +394,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
 #pragma unroll
                         for (int sp = 0; sp < 2; ++sp) {
                             const int ncol = ncol0 + sp * 32;
-                            if (ncol < args.n_valid) {
+                            if (ncol < args.n_valid && (args.scatter_c_valid == 0 || ncol % args.phase_w < args.scatter_c_valid)) {
                                 const int j = kstep & 1;
                                 uint8_t* bj = buf + j * GEMM_EPI_BUF_BYTES;
                                 const uint32_t row_s = my_row_s + j * GEMM_EPI_BUF_BYTES;
@@ -490,7 +492,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
 #pragma unroll
                         for (int sp = 0; sp < 2; ++sp) {
                             const int ncol = ncol0 + sp * 32;
-                            if (ncol < args.n_valid) {
+                            if (ncol < args.n_valid && (args.scatter_c_valid == 0 || ncol % args.phase_w < args.scatter_c_valid)) {
                                 if (has_res) {
                                     mbar_wait(my_rbar, rph);
                                     rph ^= 1;

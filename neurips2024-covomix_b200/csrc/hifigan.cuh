@@ -44,6 +44,11 @@ struct covo_hifigan {
     int mel_pad = 0;
     int is_fp16 = 0;
     bool allow_fused = true;       // COVO_HIFIGAN_NO_FUSED=1 keeps the layer-by-layer path for the last stage
+    // ConvTranspose1d layers whose output length is stride * input length (k - 2 pad == stride): "aligned polyphase" weights
+    // built once at creation (hifi_build_aligned_upconvs); null -> polyphase weights of the blob + per-element scatter epilogue
+    void* up_al[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int up_al_taps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int up_al_m0[8] = {0, 0, 0, 0, 0, 0, 0, 0};         // first tap index m (-1 when pad > 0, else 0)
     std::vector<covo::HifiPlan*> plans;
 };
 
@@ -119,6 +124,61 @@ inline ASource a3d(const void* ptr, int C, int T, int B) {
     a.row_stride = C;
     a.z_stride = static_cast<long long>(C) * T;
     return a;
+}
+
+// Aligned polyphase form of ConvTranspose1d(stride s, kernel K, padding p) with K - 2p == s (t_out == s * t_in):
+//     out[s q + rr, co] = sum_m sum_ci x[q - m, ci] W[ci, co, s m + rr + p],      m in [m0, m0 + taps)
+// so row q of the GEMM holds the s output samples s q .. s q + s - 1 and the output [B][t_out][C] is simply the GEMM's
+// [B][t_in][s * C] box -- ordinary TMA sub-tile stores, no scatter.  (The blob's polyphase form indexes phases by
+// r = (o + p) mod s, which puts sample o = s q + r - p of row q into output row q or q - 1 depending on the phase.)
+// Built from the blob's matrix pw[(r * Cop + co)][j * Cip + ci] = W[ci, co, r + s j]:  r = (rr + p) mod s, j = m + (rr + p) / s.
+__global__ void upconv_align_weights_kernel(const uint16_t* __restrict__ pw, uint16_t* __restrict__ al, int s, int pad, int J,
+                                            int taps, int m0, int cop, int cip) {
+    const long long total = static_cast<long long>(s) * cop * taps * cip;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % cip);
+        const int mt = static_cast<int>((i / cip) % taps);
+        const int co = static_cast<int>((i / (static_cast<long long>(cip) * taps)) % cop);
+        const int rr = static_cast<int>(i / (static_cast<long long>(cip) * taps * cop));
+        const int r = (rr + pad) % s, j = m0 + mt + (rr + pad) / s;
+        al[i] = (j >= 0 && j < J) ? pw[(static_cast<long long>(r) * cop + co) * (static_cast<long long>(J) * cip) + static_cast<long long>(j) * cip + ci]
+                                  : static_cast<uint16_t>(0);
+    }
+}
+
+inline bool env_flag_hifi(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+
+inline int hifi_build_aligned_upconvs(covo_hifigan* h) {
+    const covo_hifigan_cfg& c = h->cfg;
+    if (env_flag_hifi("COVO_HIFIGAN_SCATTER")) return COVO_OK;           // A/B switch: keep the scatter epilogue everywhere
+    const int hdt = h->is_fp16 ? DT_F16 : DT_BF16;
+    for (int i = 0; i < c.num_upsamples && i < 8; ++i) {
+        const int s = c.upsample_rates[i], k = c.upsample_kernel_sizes[i], pad = (k - s) / 2;
+        if (k - 2 * pad != s) continue;                                  // t_out != s * t_in (e.g. rate 5, kernel 8): scatter path
+        const int J = ceil_div(k, s), m0 = pad > 0 ? -1 : 0;
+        int m_hi = 0;                                                    // largest m with s m + rr + pad < k for some rr
+        for (int rr = 0; rr < s; ++rr) m_hi = std::max(m_hi, (k - 1 - rr - pad) / s);
+        const int taps = m_hi - m0 + 1;
+        if (taps > GEMM_MAX_TAPS) continue;
+        const int cip = pad64(hifi_chan(c, i - 1)), cop = pad64(hifi_chan(c, i));
+        Tensor tw;
+        COVO_TRY(h->w.get("ups." + std::to_string(i) + ".w", hdt, &tw));
+        if (tw.shape[0] != static_cast<int64_t>(s) * cop || tw.shape[1] != static_cast<int64_t>(J) * cip)
+            return fail(COVO_ERR_WEIGHTS, "ups.%d.w has unexpected shape", i);
+        const size_t n = static_cast<size_t>(s) * cop * taps * cip;
+        COVO_CK(cudaMalloc(&h->up_al[i], n * 2));
+        upconv_align_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256>>>(
+            tw.as<uint16_t>(), static_cast<uint16_t*>(h->up_al[i]), s, pad, J, taps, m0, cop, cip);
+        COVO_CK(cudaGetLastError());
+        h->up_al_taps[i] = taps;
+        h->up_al_m0[i] = m0;
+    }
+    COVO_CK(cudaDeviceSynchronize());
+    return COVO_OK;
 }
 
 // Conv1d(C->C_out, k, dilation d, "same" padding) as taps over time-major activations.
@@ -213,13 +273,43 @@ inline int hifi_build_ops(covo_hifigan* h, HifiPlan& p) {
             op.cat = PC_GEMM_VOC;
             ++p.launches;
         }
-        // ---- narrow last stage: one fused kernel instead of 6 * num_kernels GEMM launches + mean + conv_post
-        s.convs.clear();
-        if (i + 1 == c.num_upsamples && hifi_fused_eligible(h)) {
+        const bool fused_next = i + 1 == c.num_upsamples && hifi_fused_eligible(h);
+        if (fused_next) {
             // the fused kernel reads only the fp32 stream's first HF_C channels: the ConvTranspose1d need not write the
-            // 16-bit copy nor the padding channels (its scatter epilogue is per-element stores: 4x fewer of them)
+            // 16-bit copy nor the padding channels
             s.up.args.out_h = nullptr;
             s.up.args.scatter_c_valid = HF_C;
+        }
+        // t_out == stride * t_in: the aligned polyphase form (hifi_build_aligned_upconvs) -- an ordinary conv GEMM whose row q
+        // holds output samples stride*q .. stride*q + stride - 1, stored by the TMA sub-tile path (the per-element scatter
+        // epilogue ran these launches at ~1 TB/s of DRAM traffic)
+        if (h->up_al[i] != nullptr && s.t_out == s.stride * s.t_in) {
+            GemmOp& op = s.up;
+            const float* bias = op.args.bias;
+            void* out_h = op.args.out_h;
+            const int c_valid = op.args.scatter_c_valid;
+            const double flops = op.flops;
+            gemm_defaults(op.args);
+            COVO_TRY(build_gemm(op, h->di, a3d(in_act, s.c_in_pad, s.t_in, p.B), s.t_in, p.B, h->up_al[i], s.stride * s.c_out_pad,
+                                h->up_al_taps[i], h->is_fp16));
+            for (int mt = 0; mt < h->up_al_taps[i]; ++mt) {
+                op.args.tap_row[mt] = -(h->up_al_m0[i] + mt);
+                op.args.tap_z[mt] = 0;
+            }
+            COVO_TRY(gemm_set_outputs(op, s.x, nullptr, out_h, s.stride * s.c_out_pad, s.t_in, p.B,
+                                      static_cast<long long>(s.stride) * s.c_out_pad, static_cast<long long>(s.t_out) * s.c_out_pad,
+                                      h->is_fp16));
+            op.args.bias = bias;
+            op.args.act_h = ACT_LRELU;
+            op.args.slope = 0.1f;
+            op.args.phase_w = s.c_out_pad;
+            op.args.scatter_c_valid = c_valid;
+            op.flops = flops;
+            op.cat = PC_GEMM_VOC;
+        }
+        // ---- narrow last stage: one fused kernel instead of 6 * num_kernels GEMM launches + mean + conv_post
+        s.convs.clear();
+        if (fused_next) {
             HifiFusedArgs& f = p.fused;
             memset(&f, 0, sizeof(f));
             f.x = s.x;
