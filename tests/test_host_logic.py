@@ -71,7 +71,28 @@ def emulate_hifigan_from_blob(w, cfg, mel):
         t_in = a.shape[1]
         t_out = (t_in - 1) * u - 2 * p + k
         xs = torch.zeros(B, t_out, cop)
-        for q in range(t_in + J - 1):
+        if k - 2 * p == u:
+            # aligned polyphase form (hifigan.cuh: upconv_align_weights_kernel + the plan's tap rows): weights re-indexed
+            # from the blob's matrix as r = (rr + p) % u, j = m + (rr + p) // u; GEMM row q = output samples u*q .. u*q + u - 1
+            m0 = -1 if p > 0 else 0
+            taps = max((k - 1 - rr - p) // u for rr in range(u)) - m0 + 1
+            al = torch.zeros(u, cop, taps, cin)
+            pw = wp.reshape(u, cop, J, cin)
+            for rr in range(u):
+                for mt in range(taps):
+                    j = m0 + mt + (rr + p) // u
+                    if 0 <= j < J:
+                        al[rr, :, mt] = pw[(rr + p) % u, :, j]
+            al = al.reshape(u * cop, taps * cin)
+            assert t_out == u * t_in
+            for q in range(t_in):
+                d = bp.expand(B, -1).clone()
+                for mt in range(taps):
+                    row = q - (m0 + mt)                              # tap_row = -(m0 + mt); rows outside [0, t_in) are zero-filled
+                    if 0 <= row < t_in:
+                        d += a[:, row] @ al[:, mt * cin:(mt + 1) * cin].t()
+                xs[:, u * q:u * q + u] = d.reshape(B, u, cop)
+        for q in range(t_in + J - 1 if k - 2 * p != u else 0):
             d = bp.expand(B, -1).clone()
             for j in range(J):
                 if 0 <= q - j < t_in:
