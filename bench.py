@@ -49,9 +49,9 @@ WORKLOADS = {
                name="C4 (per GPU): CoMix T2S (1500 AR steps, 2 streams) -> VoMix 64 Euler steps -> HiFi-GAN, 30 s dialogues, batch 8"),
     # same work, software-pipelined over batches on two streams with an SM budget per stage: the latency-bound T2S loop of
     # batch i+1 (t2s_sms SMs) runs next to the flow sampler + vocoder of batch i (the remaining SMs)
-    "c4p": dict(model="vomix", B=8, N=1650, prompt=150, method="euler", n_steps=64, t2s=dict(S=200, steps=1500), t2s_sms=28,
-                name="C4 pipelined (per GPU): CoMix T2S of batch i+1 on 28 SMs || VoMix 64 Euler steps + HiFi-GAN of batch i "
-                     "on 120 SMs, 30 s dialogues, batch 8"),
+    "c4p": dict(model="vomix", B=8, N=1650, prompt=150, method="euler", n_steps=64, t2s=dict(S=200, steps=1500), t2s_sms=32,
+                name="C4 pipelined (per GPU): CoMix T2S of batch i+1 on 32 SMs || VoMix 64 Euler steps + HiFi-GAN of batch i "
+                     "on 116 SMs, 30 s dialogues, batch 8"),
 }
 
 
