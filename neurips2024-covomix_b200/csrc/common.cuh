@@ -337,6 +337,9 @@ inline int gemm_set_outputs(GemmOp& op, float* out_f32, const float* residual, v
 }
 
 inline int launch_gemm(const GemmOp& op, cudaStream_t st) {
+    // the 16-bit output is packed in the operands' format (a compile-time constant of the kernel)
+    if (op.args.has_out_h && !op.args.scatter && (op.args.h_is_fp16 != 0) != (op.fmt == 0))
+        return fail(COVO_ERR_INVALID, "GEMM 16-bit output format differs from the operand format");
     ProfScope ps(op.cat, op.flops, st);
 #define COVO_LAUNCH(BN_, F_)                                                                              \
     do {                                                                                                  \

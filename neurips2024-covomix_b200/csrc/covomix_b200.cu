@@ -606,7 +606,29 @@ int covo_dbg_gemm(const void* A_bf16, const void* W_bf16, const float* bias, con
     COVO_TRY(gemm_set_outputs(op, out_f32, residual, out_bf16, N, M, 1, N, 0, 0));
     op.args.bias = bias;
     op.args.act_h = act_h;
-    return launch_gemm(op, static_cast<cudaStream_t>(stream));
+    if (getenv("COVO_GEMM_TRACE") == nullptr) return launch_gemm(op, static_cast<cudaStream_t>(stream));
+    // debug: CTA 0's clock64 timeline of this launch (gemm_sm100.cuh, g_gemm_trace); synchronises
+    long long* d = nullptr;
+    long long hrec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int zero = 0;
+    COVO_CK(cudaMalloc(&d, 8 * 200 * sizeof(long long)));
+    COVO_CK(cudaMemset(d, 0, 8 * 200 * sizeof(long long)));
+    COVO_CK(cudaMemcpyToSymbol(g_gemm_trace, &d, sizeof(d)));
+    COVO_CK(cudaMemcpyToSymbol(g_gemm_trace_n, &zero, sizeof(zero)));
+    int rc = launch_gemm(op, static_cast<cudaStream_t>(stream));
+    cudaDeviceSynchronize();
+    cudaMemcpy(hrec, d, sizeof(hrec), cudaMemcpyDeviceToHost);
+    long long* nul = nullptr;
+    cudaMemcpyToSymbol(g_gemm_trace, &nul, sizeof(nul));
+    cudaFree(d);
+    const int m_tiles = ceil_div(M, GEMM_BM);
+    const int tiles = (op.cg == 2 || op.mc == 2) ? ceil_div(m_tiles, 2) * (N / op.bn) : m_tiles * (N / op.bn);
+    const int per_cta = ceil_div(tiles, (op.cg == 2 || op.mc == 2) ? op.grid / 2 : op.grid);
+    fprintf(stderr, "[gemm trace] M=%d N=%d K=%d bn=%d cg=%d, %d tiles on CTA 0: init %lld | first stage +%lld | last MMA issued +%lld "
+            "(%.0f cycles per tile) | last accumulator complete +%lld | its stores issued +%lld | complete +%lld | MMA thread waited "
+            "%lld cycles for accumulator buffers\n", M, N, K, op.bn, op.cg, per_cta, hrec[1] - hrec[0], hrec[2] - hrec[1], hrec[3] - hrec[2],
+            static_cast<double>(hrec[3] - hrec[2]) / per_cta, hrec[4] - hrec[3], hrec[5] - hrec[4], hrec[6] - hrec[5], hrec[7]);
+    return rc;
 }
 
 int covo_dbg_attention(const void* qkv_bf16, void* out_bf16, int Bt, int N, int heads, int impl, void* stream) {

@@ -78,7 +78,7 @@ struct GemmArgs {
 
 // Debug timeline of gemm_run (CTA 0 only; null in production): [0] entry, [1] barriers initialised, [2] first stage landed,
 // [3] last MMA issued, [4] accumulator of the last tile complete (epilogue warp 0), [5] its stores issued, [6] stores complete
-// (one 8-slot record per gemm_run call, first 200 calls)
+// [7] cycles the MMA thread spent waiting for a free accumulator buffer (one 8-slot record per gemm_run call, first 200 calls)
 __device__ long long* g_gemm_trace = nullptr;
 __device__ int g_gemm_trace_n = 0;
 #define GTR(slot) do { if (g_gemm_trace != nullptr && blockIdx.x == 0 && gtr_base >= 0) g_gemm_trace[gtr_base + (slot)] = clock64(); } while (0)
@@ -109,6 +109,41 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b, int is_fp16) {
     }
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Activation + 16-bit packing of one row's 64-column chunk.  The activation is dispatched ONCE, outside the unrolled loops, and the
+// 16-bit format is a compile-time constant: with the dispatch inside the loop every pair paid two or three uniform branches,
+// and with two or three warps per sub-partition nothing hides a branch's ~25 cycles -- the clock64 trace of the epilogue showed
+// 1 800 cycles between the accumulator load and the staging store of a plain bf16 chunk (32 conversions), 4 100 with GELU, which
+// made every K = 1024 GEMM and every narrow vocoder tile epilogue-bound (profiles/r02_gemm_epilogue_trace.txt).
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_h2c(float a, float b) {
+    if (FP16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <bool FP16>
+__device__ __forceinline__ void act_pack_chunk(uint32_t (&pk)[32], const uint32_t (&r)[64], int act_h, float slope) {
+    if (act_h == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float o0, o1;
+            gelu_fast2(o0, o1, __uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            pk[j] = pack_h2c<FP16>(o0, o1);
+        }
+    } else if (act_h == ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+            pk[j] = pack_h2c<FP16>(fmaxf(a, a * slope), fmaxf(b, b * slope));          // 0 < slope < 1
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[j] = pack_h2c<FP16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    }
 }
 
 // The persistent tile loop of one GEMM launch, callable from the stand-alone kernel below and from the persistent
@@ -246,8 +281,17 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
+            const bool tracing = g_gemm_trace != nullptr && blockIdx.x == 0 && gtr_base >= 0;
+            long long acc_stall = 0;                   // debug: cycles this thread waited for an accumulator buffer (epilogue-bound?)
             for (int tile = cta; tile < total_tiles; tile += n_ctas) {
-                mbar_wait(&tempty[as], aph ^ 1);
+                if (tracing) {
+                    const long long t0 = clock64();
+                    mbar_wait(&tempty[as], aph ^ 1);
+                    acc_stall += clock64() - t0;
+                    g_gemm_trace[gtr_base + 7] = acc_stall;
+                } else {
+                    mbar_wait(&tempty[as], aph ^ 1);
+                }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
                 for (int it = 0; it < k_iters; ++it) {
@@ -459,13 +503,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                         // 16-bit [32 x 64] sub-tile: through the buffer the last fp32 step used (the other one may hold a
                         // prefetched residual); without fp32 steps the two buffers simply alternate
                         uint32_t pk[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float o0 = __uint_as_float(r[2 * j]), o1 = __uint_as_float(r[2 * j + 1]);
-                            if (args.act_h == ACT_GELU) gelu_fast2(o0, o1, o0, o1);
-                            else if (args.act_h == ACT_LRELU) { o0 = lrelu(o0, args.slope); o1 = lrelu(o1, args.slope); }
-                            pk[j] = pack_h2(o0, o1, args.h_is_fp16);
-                        }
+                        act_pack_chunk<AB_FMT == 0>(pk, r, args.act_h, args.slope);
                         int j;
                         if (args.has_out_f32) {
                             j = (kstep - 1) & 1;
@@ -534,13 +572,7 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                     // ---------------- 16-bit output: one [32 x 64] sub-tile
                     if (args.has_out_h) {
                         uint32_t pk[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float o0 = __uint_as_float(r[2 * j]), o1 = __uint_as_float(r[2 * j + 1]);
-                            if (args.act_h == ACT_GELU) gelu_fast2(o0, o1, o0, o1);
-                            else if (args.act_h == ACT_LRELU) { o0 = lrelu(o0, args.slope); o1 = lrelu(o1, args.slope); }
-                            pk[j] = pack_h2(o0, o1, args.h_is_fp16);
-                        }
+                        act_pack_chunk<AB_FMT == 0>(pk, r, args.act_h, args.slope);
                         if (lane == 0) bulk_wait_read0();
                         __syncwarp();
 #pragma unroll

@@ -182,7 +182,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta_rank) 
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {            // arrive on an mbarrier of any CTA of the cluster
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive: what the peer is told is "my tcgen05.ld of
+    // the accumulator has completed", which tcgen05.fence::before_thread_sync orders; no generic-memory data rides on this barrier.
+    // (.release.cluster made every arrival a cluster-scope release of the thread's earlier stores: ~2 600 cycles on the epilogue's
+    // critical path of every cta_group::2 tile, profiles/r02_gemm_epilogue_trace.txt.)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
     asm volatile(
