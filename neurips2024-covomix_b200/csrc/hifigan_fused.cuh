@@ -198,12 +198,13 @@ __device__ __forceinline__ void hf_load_weights(uint16_t* Ws, const void* wg, in
 __device__ __forceinline__ void hf_wait_weights() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // The dilated-conv chain of resblock j over tile rows [mt0*16, mt1*16) (models.py:35-42); W1 must already be in flight.
-template <bool FP16, int KT>
+// INTERIOR: no row of the tile lies outside the sequence (CTA-uniform, decided once per tile) -- the per-element sequence-end
+// tests vanish from the epilogues at compile time (as uniform run-time branches they cost ~25 cycles each, 16 per conv and lane).
+template <bool FP16, int KT, bool INTERIOR>
 __device__ __forceinline__ void hf_resblock(const HifiFusedArgs& a, int j, int mt0, int mt1, int base, float* XR, uint16_t* A1,
                                             uint16_t* A2, uint16_t* W1, uint16_t* W2) {
     const int k = a.ksize[j];
-    const bool interior = base >= 0 && base + HF_R <= a.T;      // CTA-uniform: no row of the tile lies outside the sequence
-    auto in_seq = [&](int r) { const int gp = base + r; return interior || (gp >= 0 && gp < a.T); };
+    auto in_seq = [&](int r) { const int gp = base + r; return INTERIOR || (gp >= 0 && gp < a.T); };
     for (int m = 0; m < a.nd; ++m) {
         hf_wait_weights();
         __syncthreads();                              // W1 landed; A1 / XR of the previous step complete
@@ -288,13 +289,20 @@ __global__ void __launch_bounds__(HF_THREADS, 1) hifigan_fused_last_stage_kernel
             *reinterpret_cast<uint2*>(A1 + (HF_MARGIN + r) * HF_LDA + c4) = pk;
         }
         // weights stream through two buffers with cp.async: c2's arrive while c1 runs, the next c1's while c2 runs
+        const bool interior = base >= 0 && base + HF_R <= a.T;
+#define HF_RB(KT_)                                                                                   \
+    do {                                                                                             \
+        if (interior) hf_resblock<FP16, KT_, true>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2);        \
+        else hf_resblock<FP16, KT_, false>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2);                \
+    } while (0)
         switch (k) {
-            case 3: hf_resblock<FP16, 3>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
-            case 5: hf_resblock<FP16, 5>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
-            case 7: hf_resblock<FP16, 7>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
-            case 11: hf_resblock<FP16, 11>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
-            default: hf_resblock<FP16, 0>(a, j, mt0, mt1, base, XR, A1, A2, W1, W2); break;
+            case 3: HF_RB(3); break;
+            case 5: HF_RB(5); break;
+            case 7: HF_RB(7); break;
+            case 11: HF_RB(11); break;
+            default: HF_RB(0); break;
         }
+#undef HF_RB
         __syncthreads();
         // xs += resblock output over the TP + 6 rows conv_post needs
         for (int i = tid; i < (HF_TP + 6) * HF_C; i += HF_THREADS) {
