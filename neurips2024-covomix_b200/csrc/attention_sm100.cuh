@@ -27,6 +27,7 @@
 //                 tools/micro/softmax_loop.cu, profiles/r02_softmax_loop_micro.txt.
 // Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 56, softmax warpgroups 224; the pool of setmaxnreg.inc is exactly what warpgroup 0 releases)..
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace covo {
@@ -335,7 +336,11 @@ __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnAr
             const bool ho = HANDOFF > 0 && args.stagger != 0 && item.two;
             float m_run = -INFINITY;     // reference maximum of the raw scores (lags the true running max by < 2^8 / c)
             float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;     // running sum of p (four partial sums)
-            for (int j = 0; j < n_kv; ++j, ++itg) {
+            // One key tile.  MASKED: the sequence's last, partial tile (keys past N are -inf, every exponential on the MUFU) -- a
+            // compile-time variant, so that the full tiles carry neither the test nor the second copy of the exponential loop
+            // behind a run-time branch (uniform branches are not free here: one softmax warp per sub-partition and group).
+            auto key_tile = [&](auto masked_c, const int j) {
+                constexpr bool MASKED = decltype(masked_c)::value;
                 TR(0);
                 if (!s_ready) mbar_wait(&s_full[g], itg & 1);
                 TR(1);
@@ -358,8 +363,8 @@ __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnAr
                 if (lane == 0) mbar_arrive(&s_free[g]);
                 TR(2);
 
-                const int kv_valid = args.N - j * ATT_BN;      // keys >= kv_valid are padding (last tile only)
-                if (kv_valid < ATT_BN) {
+                if (MASKED) {
+                    const int kv_valid = args.N - j * ATT_BN;  // keys >= kv_valid are padding
 #pragma unroll
                     for (int i = 0; i < 128; ++i)
                         if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
@@ -400,7 +405,7 @@ __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnAr
                 // token: A's pair tile p starts after B's hand-off point of tile p-1, B's tile p after A's of tile p
                 if (ho && (g == 1 || itp > 0)) named_bar_sync64(g == 0 ? 5 + lq : 1 + lq);
                 // p = exp2(s*c - m*c) -> bf16 pairs packed in place (s[0..63] = P); the row sum is taken in fp32 before rounding
-                const bool all_mufu = (POLY_MASK == 0) || (kv_valid < ATT_BN);    // -inf scores only go through the MUFU
+                constexpr bool all_mufu = (POLY_MASK == 0) || MASKED;    // -inf scores only go through the MUFU
                 if (all_mufu) {
 #pragma unroll
                     for (int i = 0; i < 128; i += 4) {
@@ -476,6 +481,12 @@ __device__ __forceinline__ void attention_run(const AttnArgs* desc, const AttnAr
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[g]);
                 TR(6);
+            };
+            const int n_full = (args.N % ATT_BN) ? n_kv - 1 : n_kv;      // tiles without padding keys
+            for (int j = 0; j < n_full; ++j, ++itg) key_tile(std::false_type(), j);
+            if (n_full < n_kv) {
+                key_tile(std::true_type(), n_full);
+                ++itg;
             }
             // ---- item epilogue: O_g / l from TMEM (the next item's first PV product, which overwrites O_g, is only issued
             // after this thread's next p_full arrival)

@@ -229,7 +229,7 @@ __device__ __forceinline__ void mega_loop(const MegaArgs& margs, MegaOp& s_op, i
                     tc_fence_before();          // the next op reuses the TMEM columns
                     break;
                 case MOP_ATTN:
-                    attention_run<POLY_MASK, 128, ROLE, false>(&gop->a, s_op.a, smem, tmem_base, cta, n_ctas);
+                    attention_run<POLY_MASK, 0, ROLE, false>(&gop->a, s_op.a, smem, tmem_base, cta, n_ctas);
                     tc_fence_before();
                     break;
                 case MOP_NORM:

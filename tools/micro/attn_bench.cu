@@ -67,14 +67,15 @@ int main(int argc, char** argv) {
         const double flops = 4.0 * N * (double)N * 64 * H * Bt;
         const bool big = (size_t)Bt * N >= 1300;
         for (int poly = 0; poly < 3; ++poly) {
-            for (int stagger : {0, 64, 96, 128}) {        // 0: free running; else the token hand-off point (of 128 scores)
-                if (!big && stagger != 0 && stagger != 128) continue;
+            for (int stagger : {-1, 0, 64, 96, 128}) {    // -1: token code compiled out (HANDOFF = 0); 0: free running; else the token hand-off point (of 128 scores)
+                if (!big && stagger != 0 && stagger != 128 && stagger != -1) continue;
                 if (quick && poly == 0 && stagger != 0 && stagger != 128) continue;
-                a.stagger = stagger;
+                a.stagger = stagger < 0 ? 0 : stagger;
                 cudaMemset(out, 0xff, no * 2);
                 const int reps = big ? 10 : 1;
                 float ms;
-                if (stagger == 64) ms = poly == 0 ? run<0, 64>(a, reps) : (poly == 1 ? run<0x88, 64>(a, reps) : run<0x92, 64>(a, reps));
+                if (stagger == -1) ms = poly == 0 ? run<0, 0>(a, reps) : (poly == 1 ? run<0x88, 0>(a, reps) : run<0x92, 0>(a, reps));
+                else if (stagger == 64) ms = poly == 0 ? run<0, 64>(a, reps) : (poly == 1 ? run<0x88, 64>(a, reps) : run<0x92, 64>(a, reps));
                 else if (stagger == 96) ms = poly == 0 ? run<0, 96>(a, reps) : (poly == 1 ? run<0x88, 96>(a, reps) : run<0x92, 96>(a, reps));
                 else ms = poly == 0 ? run<0, 128>(a, reps) : (poly == 1 ? run<0x88, 128>(a, reps) : run<0x92, 128>(a, reps));
                 cudaMemcpy(hout.data(), out, no * 2, cudaMemcpyDeviceToHost);
