@@ -9,6 +9,8 @@ cp gpurun_out/bench_c4p.json profiles/${R}_bench_c4p_pipelined.json
 cp gpurun_out/bench_c5.jsonl profiles/${R}_bench_c5_vocoder_sweep.jsonl
 cp gpurun_out/gemm_bench.txt profiles/${R}_gemm_microbench.txt
 cp gpurun_out/gemm_epi_bench.txt profiles/${R}_gemm_epilogue_cost.txt
+[ -s gpurun_out/gemm_trace.txt ] && cp gpurun_out/gemm_trace.txt profiles/${R}_gemm_trace.txt
+[ -s gpurun_out/gemm_narrow_bench.txt ] && cp gpurun_out/gemm_narrow_bench.txt profiles/${R}_gemm_narrow_tiles.txt
 cp gpurun_out/attn_bench.txt profiles/${R}_attention_bench.txt
 cp gpurun_out/attn_trace.txt profiles/${R}_attention_trace.txt
 cp gpurun_out/flow_persistent_trace.txt profiles/${R}_flow_persistent_trace.txt

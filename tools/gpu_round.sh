@@ -14,6 +14,8 @@ timeout 600 python bench.py --workload c4p --steps 3 --warmup 3 --no-cpu-baselin
 timeout 600 python bench.py --workload c5 --steps 3 2>/dev/null | grep '^{' > gpurun_out/bench_c5.jsonl; wc -l gpurun_out/bench_c5.jsonl
 timeout 200 python tools/gemm_bench.py 2>&1 | tee gpurun_out/gemm_bench.txt | tail -3
 timeout 200 python tools/gemm_epi_bench.py 2>&1 | tee gpurun_out/gemm_epi_bench.txt | tail -3
+timeout 100 python tools/gemm_trace.py 2>&1 | grep 'gemm trace' > gpurun_out/gemm_trace.txt; wc -l gpurun_out/gemm_trace.txt
+timeout 100 python tools/gemm_narrow_bench.py > gpurun_out/gemm_narrow_bench.txt 2>&1; wc -l gpurun_out/gemm_narrow_bench.txt
 timeout 100 tools/micro/attn_bench quick 2>&1 | tee gpurun_out/attn_bench.txt | tail -3
 timeout 60 tools/micro/attn_trace 2>&1 | tee gpurun_out/attn_trace.txt | tail -3
 COVO_FLOW_PERSISTENT=1 COVO_FLOW_TRACE=1 timeout 120 python bench.py --workload c2 --steps 1 --warmup 1 --no-cpu-baseline 2>&1 | grep "flow trace" > gpurun_out/flow_persistent_trace.txt; wc -l gpurun_out/flow_persistent_trace.txt
