@@ -377,6 +377,16 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
 #pragma unroll
                 for (int j = 0; j < 16; ++j) cs4[j] = __ldg(tab + j);
             }
+            // Bias of the first chunk, fetched into the same 64 registers while the MMAs of the tile still run (no op has both
+            // RoPE and a bias); the next chunk's bias is requested as soon as this one has been added and flies under the
+            // activation and the store.  Loaded after the accumulator arrived, the 16 broadcast loads cost ~800 cycles per chunk on
+            // the epilogue's critical path (profiles/r02_gemm_epilogue_trace.txt) -- what kept FF1 epilogue-bound.
+            const bool pre_bias = args.bias != nullptr && args.rope == nullptr && rows_live;
+            if (pre_bias && n0 < args.n_valid) {
+                const float4* b4 = reinterpret_cast<const float4*>(args.bias + n0);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cs4[j] = __ldg(b4 + j);
+            }
             mbar_wait(&tfull[as], aph);
             if (e == 0 && lane == 0) GTR(4);
             tc_fence_after();
@@ -416,7 +426,24 @@ __device__ __forceinline__ void gemm_run(const GemmArgs* desc, const GemmArgs& a
                         r[j + 33] = __float_as_uint(b2 * cs.z + b1 * cs.w);
                     }
                 }
-                if (args.bias != nullptr) {
+                if (pre_bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 b = cs4[j];
+                        float s0, s1, s2, s3;
+                        add2(s0, s1, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b.x, b.y);
+                        add2(s2, s3, __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b.z, b.w);
+                        r[4 * j] = __float_as_uint(s0);
+                        r[4 * j + 1] = __float_as_uint(s1);
+                        r[4 * j + 2] = __float_as_uint(s2);
+                        r[4 * j + 3] = __float_as_uint(s3);
+                    }
+                    if (c + 1 < NCH && ncol0 + 64 < args.n_valid) {
+                        const float4* b4 = reinterpret_cast<const float4*>(args.bias + ncol0 + 64);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) cs4[j] = __ldg(b4 + j);
+                    }
+                } else if (args.bias != nullptr) {
                     const float4* b4 = reinterpret_cast<const float4*>(args.bias + ncol0);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
